@@ -1,0 +1,122 @@
+"""ctypes binding of the C-ABI library (include/amcpy_b200.h) and its in-tree build.
+
+The library is built by nvcc straight into amcpy_b200/_lib/ (git-ignored, ships to the GPU box
+with the snapshot).  There is NO CPU fallback: if the library is missing or no CUDA device is
+visible, every compute entry raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB_DIR = PKG / "_lib"
+LIB_PATH = LIB_DIR / "libamcpy_b200.so"
+HEADER = PKG.parent / "include" / "amcpy_b200.h"
+
+AMC_C64, AMC_C128 = 0, 1
+AMC_FLAG_FORCE_GENERAL = 1
+AMC_ALL_FEATURES = 0x3FFFF
+
+NVCC_FLAGS = [
+    "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+]
+
+
+class AmcError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"amcpy_b200 native error {code}: {msg}")
+        self.code = code
+
+
+def _sources():
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [HEADER]
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    built = LIB_PATH.stat().st_mtime
+    return any(s.stat().st_mtime > built for s in _sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile csrc/*.cu for sm_100a into _lib/libamcpy_b200.so (nvcc cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build the amcpy_b200 CUDA library")
+    LIB_DIR.mkdir(parents=True, exist_ok=True)
+    tmp = LIB_DIR / f".libamcpy_b200.{os.getpid()}.so"
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(tmp)] + [str(p) for p in sorted(CSRC.glob("*.cu"))]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        tmp.unlink(missing_ok=True)
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    os.replace(tmp, LIB_PATH)
+    global _LIB
+    _LIB = None
+    return LIB_PATH
+
+
+_LIB = None
+
+_P = ctypes.c_void_p
+_I64 = ctypes.c_int64
+_INT = ctypes.c_int
+_U32 = ctypes.c_uint32
+
+# name -> (restype, argtypes); must list every symbol include/amcpy_b200.h declares
+SIGNATURES = {
+    "amc_version": (_INT, []),
+    "amc_last_error_string": (ctypes.c_char_p, []),
+    "amc_device_count": (_INT, []),
+    "amc_launch_count": (_I64, []),
+    "amc_extract_batch": (_INT, [_P, _INT, _I64, _I64, _I64, _I64, _P, _I64, _U32, _INT, _P]),
+    "amc_extract_host": (_INT, [_P, _INT, _I64, _I64, _I64, _I64, _P, _I64, _U32, _INT, _INT]),
+    "amc_frames_from_sample_major": (_INT, [_P, _INT, _I64, _I64, _I64, _P, _P]),
+    "amc_instantaneous_batch": (_INT, [_P, _INT, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P]),
+    "amc_moments_batch": (_INT, [_P, _INT, _I64, _I64, _I64, _I64, _P, _P]),
+}
+
+
+def lib() -> ctypes.CDLL:
+    """Load the library (never builds implicitly; fails loudly when it is missing)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA library has not been built. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). There is no CPU fallback."
+        )
+    handle = ctypes.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = handle
+    return handle
+
+
+def check(code: int) -> None:
+    if code < 0:
+        raise AmcError(code, lib().amc_last_error_string().decode("utf-8", "replace"))
+
+
+def require_cuda() -> int:
+    """Number of devices; raises (no silent fallback) when there is none."""
+    n = lib().amc_device_count()
+    check(n)
+    return n

@@ -1,0 +1,398 @@
+// C ABI of amcpy_b200 (see include/amcpy_b200.h): argument checking, kernel selection, launches,
+// and the chunked host-buffer pipeline.  No exceptions cross the boundary; no CPU compute path.
+#include "../../include/amcpy_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <string>
+
+#include "amc_fused.cuh"
+#include "amc_general.cuh"
+
+namespace {
+
+thread_local std::string t_err;
+thread_local int64_t t_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_err = buf;
+  return code;
+}
+
+#define AMC_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(AMC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+constexpr int kMaxDevices = 64;
+std::mutex g_mu;
+bool g_tw_ready[kMaxDevices] = {};
+int g_sm_count[kMaxDevices] = {};
+
+struct DevInfo {
+  int dev;
+  int sms;
+};
+
+int device_info(DevInfo* di) {
+  int dev = 0;
+  AMC_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail(AMC_ERR_INVALID_ARG, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_sm_count[dev] == 0) {
+    int sms = 0;
+    AMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    g_sm_count[dev] = sms;
+  }
+  di->dev = dev;
+  di->sms = g_sm_count[dev];
+  return AMC_OK;
+}
+
+int ensure_twiddles(int dev, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_tw_ready[dev]) return AMC_OK;
+  amc::init_twiddle_kernel<<<amc::kTwN / 256, 256, 0, stream>>>();
+  ++t_launches;
+  AMC_CUDA(cudaGetLastError());
+  AMC_CUDA(cudaStreamSynchronize(stream));  // once per device: later calls on other streams may rely on it
+  g_tw_ready[dev] = true;
+  return AMC_OK;
+}
+
+bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+template <int N, typename CT>
+int launch_fused(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride,
+                 int sms, cudaStream_t stream) {
+  using Cfg = amc::FusedCfg<N, CT>;
+  auto kern = amc::fused_features_kernel<N, CT>;
+  static thread_local int blocks_per_sm[kMaxDevices] = {};
+  int dev = 0;
+  AMC_CUDA(cudaGetDevice(&dev));
+  if (blocks_per_sm[dev] == 0) {
+    AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int occ = 0;
+    AMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::CTA, Cfg::SMEM_BYTES));
+    if (occ < 1) return fail(AMC_ERR_CUDA, "fused kernel N=%d does not fit on this device", N);
+    blocks_per_sm[dev] = occ;
+  }
+  const int64_t want = (n_frames + Cfg::G - 1) / Cfg::G;
+  const int64_t cap = static_cast<int64_t>(sms) * blocks_per_sm[dev];
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  kern<<<grid, Cfg::CTA, Cfg::SMEM_BYTES, stream>>>(static_cast<const CT*>(iq), n_frames, frame_stride, out,
+                                                   out_stride);
+  ++t_launches;
+  AMC_CUDA(cudaGetLastError());
+  return AMC_OK;
+}
+
+template <typename CT>
+int dispatch_fused(int64_t n, const void* iq, int64_t n_frames, int64_t frame_stride, double* out,
+                   int64_t out_stride, int sms, cudaStream_t stream) {
+  switch (n) {
+    case 256: return launch_fused<256, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+    case 512: return launch_fused<512, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+    case 1024: return launch_fused<1024, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+    case 2048: return launch_fused<2048, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+    case 4096: return launch_fused<4096, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+    default: return fail(AMC_ERR_UNSUPPORTED, "no fused kernel for frame_size %lld", static_cast<long long>(n));
+  }
+}
+
+bool fused_size(int64_t n) { return n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096; }
+
+constexpr int64_t kGeneralPow2Max = 16384;   // N float2 of FFT scratch must fit in shared memory
+constexpr int64_t kGeneralDftMax = 12288;    // N double2 of twiddles must fit in shared memory
+
+template <typename CT>
+int launch_general(const void* iq, int64_t n_frames, int64_t n, int64_t frame_stride, int64_t sample_stride,
+                   double* out, int64_t out_stride, int sms, cudaStream_t stream) {
+  int fft_mode;
+  size_t dyn;
+  if (is_pow2(n) && n >= 2) {
+    if (n > kGeneralPow2Max)
+      return fail(AMC_ERR_UNSUPPORTED, "power-of-two frame_size %lld > %lld not supported", (long long)n,
+                  (long long)kGeneralPow2Max);
+    fft_mode = 1;
+    dyn = static_cast<size_t>(n) * sizeof(float2);
+  } else {
+    if (n > kGeneralDftMax)
+      return fail(AMC_ERR_UNSUPPORTED, "non-power-of-two frame_size %lld > %lld not supported", (long long)n,
+                  (long long)kGeneralDftMax);
+    fft_mode = 0;
+    dyn = static_cast<size_t>(n) * sizeof(double2);
+  }
+  auto kern = amc::general_features_kernel<CT>;
+  AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int64_t cap = static_cast<int64_t>(sms) * 4;
+  const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
+  kern<<<grid, amc::kGenThreads, dyn, stream>>>(static_cast<const CT*>(iq), n_frames, static_cast<int>(n),
+                                               frame_stride, sample_stride, out, out_stride, fft_mode);
+  ++t_launches;
+  AMC_CUDA(cudaGetLastError());
+  return AMC_OK;
+}
+
+int check_common(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size, int64_t frame_stride,
+                 int64_t sample_stride) {
+  if (iq_dtype != AMC_C64 && iq_dtype != AMC_C128) return fail(AMC_ERR_INVALID_ARG, "iq_dtype %d unknown", iq_dtype);
+  if (n_frames < 0) return fail(AMC_ERR_INVALID_ARG, "n_frames %lld < 0", (long long)n_frames);
+  if (frame_size < 1) return fail(AMC_ERR_INVALID_ARG, "frame_size %lld < 1", (long long)frame_size);
+  if (frame_size > (1 << 30)) return fail(AMC_ERR_UNSUPPORTED, "frame_size %lld too large", (long long)frame_size);
+  if (n_frames > 0 && iq == nullptr) return fail(AMC_ERR_INVALID_ARG, "iq is NULL");
+  if (sample_stride < 1) return fail(AMC_ERR_INVALID_ARG, "sample_stride %lld < 1", (long long)sample_stride);
+  if (frame_stride < 0) return fail(AMC_ERR_INVALID_ARG, "frame_stride %lld < 0", (long long)frame_stride);
+  return AMC_OK;
+}
+
+// ---------------------------------------------------------------- host pipeline state (per device)
+struct HostPipe {
+  bool ready = false;
+  cudaStream_t stream[2] = {nullptr, nullptr};
+  void* d_in[2] = {nullptr, nullptr};
+  void* d_tr[2] = {nullptr, nullptr};   // transposed copy for sample-major input
+  double* d_out[2] = {nullptr, nullptr};
+  size_t in_bytes = 0, tr_bytes = 0, out_bytes = 0;
+};
+HostPipe g_pipe[kMaxDevices];
+std::mutex g_pipe_mu[kMaxDevices];
+
+int ensure_pipe(HostPipe& p, size_t in_bytes, size_t tr_bytes, size_t out_bytes) {
+  if (!p.ready) {
+    for (int i = 0; i < 2; ++i) AMC_CUDA(cudaStreamCreateWithFlags(&p.stream[i], cudaStreamNonBlocking));
+    p.ready = true;
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (p.in_bytes < in_bytes) {
+      if (p.d_in[i]) AMC_CUDA(cudaFree(p.d_in[i]));
+      p.d_in[i] = nullptr;
+      AMC_CUDA(cudaMalloc(&p.d_in[i], in_bytes));
+    }
+    if (p.tr_bytes < tr_bytes) {
+      if (p.d_tr[i]) AMC_CUDA(cudaFree(p.d_tr[i]));
+      p.d_tr[i] = nullptr;
+      AMC_CUDA(cudaMalloc(&p.d_tr[i], tr_bytes));
+    }
+    if (p.out_bytes < out_bytes) {
+      if (p.d_out[i]) AMC_CUDA(cudaFree(p.d_out[i]));
+      p.d_out[i] = nullptr;
+      AMC_CUDA(cudaMalloc(reinterpret_cast<void**>(&p.d_out[i]), out_bytes));
+    }
+  }
+  if (p.in_bytes < in_bytes) p.in_bytes = in_bytes;
+  if (p.tr_bytes < tr_bytes) p.tr_bytes = tr_bytes;
+  if (p.out_bytes < out_bytes) p.out_bytes = out_bytes;
+  return AMC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int amc_version(void) { return 1000; }
+
+const char* amc_last_error_string(void) { return t_err.c_str(); }
+
+int64_t amc_launch_count(void) { return t_launches; }
+
+int amc_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    return fail(AMC_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  }
+  return n;
+}
+
+int amc_extract_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size, int64_t frame_stride,
+                      int64_t sample_stride, double* out, int64_t out_stride, uint32_t feature_mask, int flags,
+                      void* cuda_stream) {
+  int rc = check_common(iq, iq_dtype, n_frames, frame_size, frame_stride, sample_stride);
+  if (rc != AMC_OK) return rc;
+  if ((feature_mask & AMC_ALL_FEATURES) == 0) return fail(AMC_ERR_INVALID_ARG, "feature_mask selects nothing");
+  if (out_stride < AMC_N_FEATURES) return fail(AMC_ERR_INVALID_ARG, "out_stride %lld < 18", (long long)out_stride);
+  if (n_frames == 0) return AMC_OK;
+  if (out == nullptr) return fail(AMC_ERR_INVALID_ARG, "out is NULL");
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  DevInfo di;
+  rc = device_info(&di);
+  if (rc != AMC_OK) return rc;
+
+  const size_t elt = iq_dtype == AMC_C128 ? 16 : 8;
+  const bool aligned = (reinterpret_cast<uintptr_t>(iq) % 16 == 0) && ((frame_stride * elt) % 16 == 0);
+  const bool fused = !(flags & AMC_FLAG_FORCE_GENERAL) && sample_stride == 1 && fused_size(frame_size) && aligned &&
+                     (frame_stride >= frame_size || n_frames == 1);
+  if (fused) {
+    rc = ensure_twiddles(di.dev, stream);
+    if (rc != AMC_OK) return rc;
+    if (iq_dtype == AMC_C128)
+      return dispatch_fused<double2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream);
+    return dispatch_fused<float2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream);
+  }
+  if (iq_dtype == AMC_C128)
+    return launch_general<double2>(iq, n_frames, frame_size, frame_stride, sample_stride, out, out_stride, di.sms,
+                                   stream);
+  return launch_general<float2>(iq, n_frames, frame_size, frame_stride, sample_stride, out, out_stride, di.sms,
+                                stream);
+}
+
+int amc_frames_from_sample_major(const void* src, int iq_dtype, int64_t n_frames, int64_t frame_size,
+                                 int64_t src_sample_stride, void* dst, void* cuda_stream) {
+  int rc = check_common(src, iq_dtype, n_frames, frame_size, 1, src_sample_stride);
+  if (rc != AMC_OK) return rc;
+  if (n_frames == 0) return AMC_OK;
+  if (dst == nullptr) return fail(AMC_ERR_INVALID_ARG, "dst is NULL");
+  if (src_sample_stride < n_frames) return fail(AMC_ERR_INVALID_ARG, "src_sample_stride < n_frames");
+  if (frame_size > 65535LL * 32) return fail(AMC_ERR_UNSUPPORTED, "frame_size too large for the re-layout grid");
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  dim3 grid(static_cast<unsigned>((n_frames + 31) / 32), static_cast<unsigned>((frame_size + 31) / 32));
+  if (iq_dtype == AMC_C128)
+    amc::frames_from_sample_major_kernel<double2><<<grid, 256, 0, stream>>>(
+        static_cast<const double2*>(src), n_frames, static_cast<int>(frame_size), src_sample_stride,
+        static_cast<double2*>(dst));
+  else
+    amc::frames_from_sample_major_kernel<float2><<<grid, 256, 0, stream>>>(
+        static_cast<const float2*>(src), n_frames, static_cast<int>(frame_size), src_sample_stride,
+        static_cast<float2*>(dst));
+  ++t_launches;
+  AMC_CUDA(cudaGetLastError());
+  return AMC_OK;
+}
+
+int amc_instantaneous_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size, int64_t frame_stride,
+                            int64_t sample_stride, double* abs_out, double* phase_out, double* unwrapped_out,
+                            double* frequency_out, double* cn_amplitude_out, void* cuda_stream) {
+  int rc = check_common(iq, iq_dtype, n_frames, frame_size, frame_stride, sample_stride);
+  if (rc != AMC_OK) return rc;
+  if (n_frames == 0) return AMC_OK;
+  DevInfo di;
+  rc = device_info(&di);
+  if (rc != AMC_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const int64_t cap = static_cast<int64_t>(di.sms) * 8;
+  const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
+  if (iq_dtype == AMC_C128)
+    amc::instantaneous_kernel<double2><<<grid, amc::kGenThreads, 0, stream>>>(
+        static_cast<const double2*>(iq), n_frames, static_cast<int>(frame_size), frame_stride, sample_stride, abs_out,
+        phase_out, unwrapped_out, frequency_out, cn_amplitude_out);
+  else
+    amc::instantaneous_kernel<float2><<<grid, amc::kGenThreads, 0, stream>>>(
+        static_cast<const float2*>(iq), n_frames, static_cast<int>(frame_size), frame_stride, sample_stride, abs_out,
+        phase_out, unwrapped_out, frequency_out, cn_amplitude_out);
+  ++t_launches;
+  AMC_CUDA(cudaGetLastError());
+  return AMC_OK;
+}
+
+int amc_moments_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size, int64_t frame_stride,
+                      int64_t sample_stride, double* out, void* cuda_stream) {
+  int rc = check_common(iq, iq_dtype, n_frames, frame_size, frame_stride, sample_stride);
+  if (rc != AMC_OK) return rc;
+  if (n_frames == 0) return AMC_OK;
+  if (out == nullptr) return fail(AMC_ERR_INVALID_ARG, "out is NULL");
+  DevInfo di;
+  rc = device_info(&di);
+  if (rc != AMC_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const int64_t cap = static_cast<int64_t>(di.sms) * 8;
+  const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
+  if (iq_dtype == AMC_C128)
+    amc::moments_kernel<double2><<<grid, amc::kGenThreads, 0, stream>>>(
+        static_cast<const double2*>(iq), n_frames, static_cast<int>(frame_size), frame_stride, sample_stride, out);
+  else
+    amc::moments_kernel<float2><<<grid, amc::kGenThreads, 0, stream>>>(
+        static_cast<const float2*>(iq), n_frames, static_cast<int>(frame_size), frame_stride, sample_stride, out);
+  ++t_launches;
+  AMC_CUDA(cudaGetLastError());
+  return AMC_OK;
+}
+
+int amc_extract_host(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size, int64_t frame_stride,
+                     int64_t sample_stride, double* out, int64_t out_stride, uint32_t feature_mask, int flags,
+                     int device) {
+  int rc = check_common(iq, iq_dtype, n_frames, frame_size, frame_stride, sample_stride);
+  if (rc != AMC_OK) return rc;
+  if ((feature_mask & AMC_ALL_FEATURES) == 0) return fail(AMC_ERR_INVALID_ARG, "feature_mask selects nothing");
+  if (out_stride < AMC_N_FEATURES) return fail(AMC_ERR_INVALID_ARG, "out_stride %lld < 18", (long long)out_stride);
+  if (n_frames == 0) return AMC_OK;
+  if (out == nullptr) return fail(AMC_ERR_INVALID_ARG, "out is NULL");
+  const bool row_major = sample_stride == 1 && (frame_stride >= frame_size || n_frames == 1);
+  const bool sample_major = !row_major && frame_stride == 1 && sample_stride >= n_frames;
+  if (!row_major && !sample_major)
+    return fail(AMC_ERR_UNSUPPORTED,
+                "host layout must be row-per-frame (sample_stride 1) or sample-major (frame_stride 1)");
+  if (device < 0 || device >= kMaxDevices) return fail(AMC_ERR_INVALID_ARG, "device %d out of range", device);
+  int prev = 0;
+  AMC_CUDA(cudaGetDevice(&prev));
+  AMC_CUDA(cudaSetDevice(device));
+
+  const size_t elt = iq_dtype == AMC_C128 ? 16 : 8;
+  const size_t frame_bytes = static_cast<size_t>(frame_size) * elt;
+  // ~64 MiB of samples per chunk, a multiple of 32 frames, at least 32
+  int64_t chunk = static_cast<int64_t>((64u << 20) / frame_bytes);
+  chunk = chunk < 32 ? 32 : (chunk / 32) * 32;
+  if (chunk > n_frames) chunk = n_frames;
+
+  std::lock_guard<std::mutex> lk(g_pipe_mu[device]);
+  HostPipe& p = g_pipe[device];
+  rc = ensure_pipe(p, static_cast<size_t>(chunk) * frame_bytes, sample_major ? static_cast<size_t>(chunk) * frame_bytes : 0,
+                   static_cast<size_t>(chunk) * AMC_N_FEATURES * sizeof(double));
+  if (rc != AMC_OK) {
+    cudaSetDevice(prev);
+    return rc;
+  }
+  const unsigned char* src = static_cast<const unsigned char*>(iq);
+  int status = AMC_OK;
+  int64_t c = 0;
+  for (int64_t f0 = 0; f0 < n_frames && status == AMC_OK; f0 += chunk, ++c) {
+    const int b = static_cast<int>(c & 1);
+    const int64_t nf = (n_frames - f0) < chunk ? (n_frames - f0) : chunk;
+    cudaStream_t st = p.stream[b];
+    cudaError_t e;
+    const void* dev_frames = p.d_in[b];
+    if (row_major) {
+      e = cudaMemcpy2DAsync(p.d_in[b], frame_bytes, src + static_cast<size_t>(f0) * frame_stride * elt,
+                            static_cast<size_t>(frame_stride) * elt, frame_bytes, static_cast<size_t>(nf),
+                            cudaMemcpyHostToDevice, st);
+    } else {
+      e = cudaMemcpy2DAsync(p.d_in[b], static_cast<size_t>(nf) * elt, src + static_cast<size_t>(f0) * elt,
+                            static_cast<size_t>(sample_stride) * elt, static_cast<size_t>(nf) * elt,
+                            static_cast<size_t>(frame_size), cudaMemcpyHostToDevice, st);
+    }
+    if (e != cudaSuccess) {
+      status = fail(AMC_ERR_CUDA, "host->device copy failed: %s", cudaGetErrorString(e));
+      break;
+    }
+    if (sample_major) {
+      status = amc_frames_from_sample_major(p.d_in[b], iq_dtype, nf, frame_size, nf, p.d_tr[b], st);
+      if (status != AMC_OK) break;
+      dev_frames = p.d_tr[b];
+    }
+    status = amc_extract_batch(dev_frames, iq_dtype, nf, frame_size, frame_size, 1, p.d_out[b], AMC_N_FEATURES,
+                               feature_mask, flags, st);
+    if (status != AMC_OK) break;
+    e = cudaMemcpy2DAsync(out + f0 * out_stride, static_cast<size_t>(out_stride) * sizeof(double), p.d_out[b],
+                          AMC_N_FEATURES * sizeof(double), AMC_N_FEATURES * sizeof(double), static_cast<size_t>(nf),
+                          cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) status = fail(AMC_ERR_CUDA, "device->host copy failed: %s", cudaGetErrorString(e));
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaStreamSynchronize(p.stream[i]);
+    if (e != cudaSuccess && status == AMC_OK)
+      status = fail(AMC_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
+  }
+  cudaSetDevice(prev);
+  return status;
+}
+
+}  // extern "C"

@@ -1,0 +1,336 @@
+// General kernels: any frame length >= 1, any element strides, complex64 or complex128.
+// One CTA (256 threads) per frame, float64 arithmetic with the reference's exact unwrap rules;
+// used for every shape the fused kernel does not cover (ragged sizes, strided / sample-major
+// views, the reference's 10-sample fixture) and for the helper value types.
+#pragma once
+#include "amc_device.cuh"
+
+namespace amc {
+
+constexpr int kGenThreads = 256;
+constexpr int kGenWarps = kGenThreads / 32;
+
+template <typename CT>
+__device__ __forceinline__ void load_strided(const CT* __restrict__ base, int64_t n, int64_t sample_stride,
+                                             double& a, double& b) {
+  const CT v = base[n * sample_stride];
+  a = static_cast<double>(v.x);
+  b = static_cast<double>(v.y);
+}
+
+// Sum V doubles over the CTA; every thread receives the totals.  Fixed order (reproducible).
+// red: shared double[kGenWarps * V].
+template <int V>
+__device__ __forceinline__ void block_sum(double (&v)[V], double* red, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) x += __shfl_xor_sync(0xffffffffu, x, w);
+    if (lane == 0) red[warp * V + i] = x;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kGenWarps; ++w) s += red[w * V + i];
+    v[i] = s;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double block_max(double x, double* red, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, w));
+  if (lane == 0) red[warp] = x;
+  __syncthreads();
+  double m = red[0];
+#pragma unroll
+  for (int w = 1; w < kGenWarps; ++w) m = fmax(m, red[w]);
+  __syncthreads();
+  return m;
+}
+
+// fft_mode: 0 = direct DFT (float64, twiddle table of N double2 in dynamic smem),
+//           1 = power-of-two in-place radix-2 DIF (float32, N float2 in dynamic smem)
+template <typename CT>
+__global__ void __launch_bounds__(kGenThreads)
+general_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int64_t frame_stride,
+                        int64_t sample_stride, double* __restrict__ out, int64_t out_stride, int fft_mode) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ double red[kGenWarps * 20];
+  const int tid = threadIdx.x;
+
+  if (fft_mode == 0) {  // twiddle table once per CTA
+    double2* tw = reinterpret_cast<double2*>(dyn);
+    for (int m = tid; m < n; m += kGenThreads) {
+      double s, c;
+      sincospi(-2.0 * static_cast<double>(m) / static_cast<double>(n), &s, &c);
+      tw[m] = make_double2(c, s);
+    }
+    __syncthreads();
+  }
+
+  for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
+    const CT* base = iq + f * frame_stride;
+
+    // ---- pass 1: raw sums -----------------------------------------------------------
+    Monomials mono;
+    mono.clear();
+    double sr = 0.0, sph = 0.0, saph = 0.0, sfq = 0.0;
+    for (int i = tid; i < n; i += kGenThreads) {
+      double a, b;
+      load_strided(base, i, sample_stride, a, b);
+      mono.add(a, b);
+      sr += hypot(a, b);                              // np.abs == hypot (features.py:27)
+      const double p0 = atan2_exact(b, a);            // np.angle  (features.py:28)
+      sph += p0;
+      saph += fabs(p0);
+      if (i + 1 < n) {
+        double a1, b1;
+        load_strided(base, i + 1, sample_stride, a1, b1);
+        sfq += unwrap_step(atan2_exact(b1, a1) - p0) / kTwoPi;   // features.py:29-30
+      }
+    }
+    double v1[19];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) v1[i] = mono.s[i];
+    v1[15] = sr;
+    v1[16] = sph;
+    v1[17] = saph;
+    v1[18] = sfq;
+    block_sum<19>(v1, red, tid);
+    const double dn = static_cast<double>(n);
+    const double mu_r = v1[15] / dn, mu_ph = v1[16] / dn, mu_aph = v1[17] / dn;
+    const double mu_f = v1[18] / (dn - 1.0);
+
+    // ---- pass 2: centred sums ---------------------------------------------------------
+    double v2[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < n; i += kGenThreads) {
+      double a, b;
+      load_strided(base, i, sample_stride, a, b);
+      const double d = hypot(a, b) - mu_r;
+      const double d2 = d * d;
+      v2[0] += fabs(d);
+      v2[1] += d2;
+      v2[2] += d2 * d2;
+      const double p0 = atan2_exact(b, a);
+      const double e = p0 - mu_ph, ea = fabs(p0) - mu_aph;
+      v2[3] += e * e;
+      v2[4] += ea * ea;
+      if (i + 1 < n) {
+        double a1, b1;
+        load_strided(base, i + 1, sample_stride, a1, b1);
+        const double ef = unwrap_step(atan2_exact(b1, a1) - p0) / kTwoPi - mu_f;
+        const double ef2 = ef * ef;
+        v2[5] += ef2;
+        v2[6] += ef2 * ef2;
+      }
+    }
+    block_sum<7>(v2, red, tid);
+
+    // ---- spectrum max -----------------------------------------------------------------
+    double smax = 0.0;
+    if (fft_mode == 1) {
+      float2* buf = reinterpret_cast<float2*>(dyn);
+      for (int i = tid; i < n; i += kGenThreads) {
+        double a, b;
+        load_strided(base, i, sample_stride, a, b);
+        buf[i] = make_float2(static_cast<float>(a), static_cast<float>(b));
+      }
+      __syncthreads();
+      for (int half = n >> 1; half >= 1; half >>= 1) {
+        const float inv_half = 1.0f / static_cast<float>(half);
+        for (int p = tid; p < (n >> 1); p += kGenThreads) {
+          const int off = p & (half - 1);
+          const int i0 = ((p - off) << 1) + off;
+          const float2 u = buf[i0], w = buf[i0 + half];
+          buf[i0] = make_float2(u.x + w.x, u.y + w.y);
+          const float dx = u.x - w.x, dy = u.y - w.y;
+          float sn, cs;
+          sincospif(-static_cast<float>(off) * inv_half, &sn, &cs);
+          buf[i0 + half] = make_float2(dx * cs - dy * sn, dx * sn + dy * cs);
+        }
+        __syncthreads();
+      }
+      for (int i = tid; i < n; i += kGenThreads) {
+        const float2 u = buf[i];
+        smax = fmax(smax, static_cast<double>(u.x) * u.x + static_cast<double>(u.y) * u.y);
+      }
+      __syncthreads();
+    } else {
+      const double2* tw = reinterpret_cast<const double2*>(dyn);
+      for (int k = tid; k < n; k += kGenThreads) {
+        double xr = 0.0, xi = 0.0;
+        int idx = 0;
+        for (int i = 0; i < n; ++i) {
+          double a, b;
+          load_strided(base, i, sample_stride, a, b);
+          const double2 w = tw[idx];
+          xr += a * w.x - b * w.y;
+          xi += a * w.y + b * w.x;
+          idx += k;
+          if (idx >= n) idx -= n;
+        }
+        smax = fmax(smax, xr * xr + xi * xi);
+      }
+    }
+    smax = block_max(smax, red, tid);
+
+    if (tid == 0) {
+      FrameSums fs;
+#pragma unroll
+      for (int i = 0; i < 15; ++i) fs.mono[i] = v1[i];
+      fs.sum_r = v1[15];
+      fs.c_abs1 = v2[0];
+      fs.c2 = v2[1];
+      fs.c4 = v2[2];
+      fs.ph_m2 = v2[3];
+      fs.aph_m2 = v2[4];
+      fs.f_m2 = v2[5];
+      fs.f_m4 = v2[6];
+      fs.mean_f = mu_f;
+      fs.spec_max = smax;
+      double res[18];
+      finalize_features(fs, n, res);
+#pragma unroll
+      for (int i = 0; i < 18; ++i) out[f * out_stride + i] = res[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ MomentValues (features.py:39-58)
+template <typename CT>
+__global__ void __launch_bounds__(kGenThreads)
+moments_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int64_t frame_stride, int64_t sample_stride,
+               double* __restrict__ out) {
+  __shared__ double red[kGenWarps * 15];
+  const int tid = threadIdx.x;
+  for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
+    const CT* base = iq + f * frame_stride;
+    Monomials mono;
+    mono.clear();
+    for (int i = tid; i < n; i += kGenThreads) {
+      double a, b;
+      load_strided(base, i, sample_stride, a, b);
+      mono.add(a, b);
+    }
+    block_sum<15>(mono.s, red, tid);
+    if (tid == 0) {
+      const Moments m = moments_from_monomials(mono.s, 1.0 / static_cast<double>(n));
+      double* o = out + f * 22;
+      const Cplx list[11] = {m.m20, {m.m21, 0.0}, m.m22, m.m40, m.m41, {m.m42, 0.0}, m.m43,
+                             m.m60, m.m61, {m.m62, 0.0}, m.m63};
+#pragma unroll
+      for (int i = 0; i < 11; ++i) {
+        o[2 * i] = list[i].re;
+        o[2 * i + 1] = list[i].im;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ InstantaneousValues (features.py:17-31)
+// unwrapped = phase + cumsum(ph_correct): block-wide inclusive scan of the 2*pi corrections
+// (warp shuffles + one cross-warp step), carried across 256-sample chunks.
+template <typename CT>
+__global__ void __launch_bounds__(kGenThreads)
+instantaneous_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int64_t frame_stride,
+                     int64_t sample_stride, double* __restrict__ abs_out, double* __restrict__ phase_out,
+                     double* __restrict__ unwrapped_out, double* __restrict__ freq_out,
+                     double* __restrict__ cna_out) {
+  __shared__ double red[kGenWarps * 2];
+  __shared__ double warp_tot[kGenWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
+    const CT* base = iq + f * frame_stride;
+    double carry = 0.0;      // cumsum of corrections over previous chunks
+    double sum_abs = 0.0;
+    for (int c0 = 0; c0 < n; c0 += kGenThreads) {
+      const int i = c0 + tid;
+      double p = 0.0, corr = 0.0, r = 0.0;
+      if (i < n) {
+        double a, b;
+        load_strided(base, i, sample_stride, a, b);
+        r = hypot(a, b);
+        p = atan2_exact(b, a);
+        if (i > 0) {
+          double a0, b0;
+          load_strided(base, i - 1, sample_stride, a0, b0);
+          const double dd = p - atan2_exact(b0, a0);
+          corr = unwrap_step(dd) - dd;    // ph_correct (0 when |dd| < pi)
+        }
+        sum_abs += r;
+        if (abs_out) abs_out[f * n + i] = r;
+        if (phase_out) phase_out[f * n + i] = p;
+      }
+      // inclusive scan of corr over the chunk
+      double x = corr;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+      }
+      if (lane == 31) warp_tot[warp] = x;
+      __syncthreads();
+      double off = carry;
+      for (int w = 0; w < warp; ++w) off += warp_tot[w];
+      double chunk_tot = 0.0;
+      for (int w = 0; w < kGenWarps; ++w) chunk_tot += warp_tot[w];
+      const double cum = off + x;        // cumsum(ph_correct) up to and including sample i
+      if (i < n) {
+        const double up = p + cum;
+        if (unwrapped_out) unwrapped_out[f * n + i] = up;
+        if (freq_out && i > 0) {
+          // diff(unwrapped)/(2*pi): previous unwrapped value = p_prev + (cum - corr)
+          double a0, b0;
+          load_strided(base, i - 1, sample_stride, a0, b0);
+          const double up_prev = atan2_exact(b0, a0) + (cum - corr);
+          freq_out[f * (n - 1) + (i - 1)] = (up - up_prev) / kTwoPi;
+        }
+      }
+      carry += chunk_tot;
+      __syncthreads();
+    }
+    double v[2] = {sum_abs, 0.0};
+    block_sum<2>(v, red, tid);
+    if (cna_out) {
+      const double mean = v[0] / static_cast<double>(n);
+      for (int i = tid; i < n; i += kGenThreads) {
+        double a, b;
+        load_strided(base, i, sample_stride, a, b);
+        cna_out[f * n + i] = hypot(a, b) / mean - 1.0;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ sample-major -> one row per frame
+// src element (f, n) at f + n*src_sample_stride; dst (f, n) at f*N + n.  32x32 tiles through smem.
+template <typename CT>
+__global__ void __launch_bounds__(256)
+frames_from_sample_major_kernel(const CT* __restrict__ src, int64_t n_frames, int n, int64_t src_sample_stride,
+                                CT* __restrict__ dst) {
+  __shared__ CT tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int64_t f0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int n0 = blockIdx.y * 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int nn = n0 + ty + 8 * k;
+    const int64_t ff = f0 + tx;
+    if (nn < n && ff < n_frames) tile[ty + 8 * k][tx] = src[static_cast<int64_t>(nn) * src_sample_stride + ff];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t ff = f0 + ty + 8 * k;
+    const int nn = n0 + tx;
+    if (nn < n && ff < n_frames) dst[ff * n + nn] = tile[tx][ty + 8 * k];
+  }
+}
+
+}  // namespace amc

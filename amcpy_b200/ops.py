@@ -1,0 +1,171 @@
+"""Batched operators over the C ABI: the reference's per-frame operator
+(/root/reference/src/amcpy/features.py:214-232) applied to whole (n_snr, n_frames, frame_size)
+tensors at once.  torch is used for device memory and streams only."""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _native as nat
+
+N_FEATURES = 18
+MOMENT_NAMES = ("m20", "m21", "m22", "m40", "m41", "m42", "m43", "m60", "m61", "m62", "m63")
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _dtype_code(t) -> int:
+    torch = _torch()
+    if t.dtype == torch.complex128:
+        return nat.AMC_C128
+    if t.dtype == torch.complex64:
+        return nat.AMC_C64
+    raise TypeError(f"expected a complex64/complex128 tensor, got {t.dtype}")
+
+
+def _as_frames_2d(iq):
+    """(..., N) CUDA tensor -> 2-D view (frames, N) without copying when the leading dims collapse."""
+    torch = _torch()
+    if not iq.is_cuda:
+        raise ValueError("extract_features needs a CUDA tensor (use extract_features_host for host arrays)")
+    if iq.dim() == 1:
+        iq = iq.unsqueeze(0)
+    n = iq.shape[-1]
+    if iq.dim() == 2:
+        return iq
+    try:
+        return iq.view(-1, n)
+    except RuntimeError:
+        return iq.reshape(-1, n)  # copies only when the leading dims are not collapsible
+
+
+def _stream_ptr(stream):
+    torch = _torch()
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return s.cuda_stream
+
+
+def extract_features(iq, out=None, stream=None, force_general: bool = False, feature_mask: int = nat.AMC_ALL_FEATURES):
+    """All 18 features of every frame of a device-resident complex tensor.
+
+    iq  : CUDA tensor (..., frame_size), complex128 or complex64 (north_star's batched entry takes
+          (n_snr, n_frames, frame_size)).
+    out : optional CUDA float64 tensor (..., 18), C-contiguous.
+    Returns float64 (..., 18); column k = feature id k+1.  Enqueued on `stream`
+    (default: torch's current stream); does not synchronise.
+    """
+    torch = _torch()
+    lead = tuple(iq.shape[:-1]) if iq.dim() > 1 else (1,)
+    x = _as_frames_2d(iq)
+    n_frames, n = x.shape
+    if out is None:
+        out = torch.empty((n_frames, N_FEATURES), dtype=torch.float64, device=x.device)
+    else:
+        if out.dtype != torch.float64 or not out.is_contiguous() or out.numel() != n_frames * N_FEATURES:
+            raise ValueError("out must be a contiguous float64 tensor with 18 values per frame")
+    with torch.cuda.device(x.device):
+        rc = nat.lib().amc_extract_batch(
+            x.data_ptr(), _dtype_code(x), n_frames, n, x.stride(0) if n_frames > 1 else n, x.stride(1) if n > 1 else 1,
+            out.data_ptr(), N_FEATURES, feature_mask, nat.AMC_FLAG_FORCE_GENERAL if force_general else 0,
+            _stream_ptr(stream),
+        )
+    nat.check(rc)
+    return out.view(*lead, N_FEATURES) if iq.dim() > 1 else out.view(N_FEATURES)
+
+
+def _np_dtype_code(a: np.ndarray) -> int:
+    if a.dtype == np.complex128:
+        return nat.AMC_C128
+    if a.dtype == np.complex64:
+        return nat.AMC_C64
+    raise TypeError(f"expected complex64/complex128, got {a.dtype}")
+
+
+def extract_features_host(frames: np.ndarray, device: int = 0, out: np.ndarray | None = None,
+                          force_general: bool = False) -> np.ndarray:
+    """Host arrays through the library's chunked copy/compute pipeline (amc_extract_host).
+
+    frames: (n_frames, N) complex array.  Row-per-frame (C order, rows may be padded) and
+    sample-major (Fortran order - what scipy.io.loadmat returns) are consumed in place; any other
+    striding is made C-contiguous first.  Returns float64 (n_frames, 18)."""
+    a = np.asarray(frames)
+    if a.ndim == 1:
+        a = a[None, :]
+    if a.ndim != 2:
+        raise ValueError("frames must be 2-D (n_frames, frame_size)")
+    if not np.iscomplexobj(a):
+        a = a.astype(np.complex128)
+    code = _np_dtype_code(a)
+    nf, n = a.shape
+    es = a.itemsize
+    s0, s1 = a.strides[0] // es, a.strides[1] // es
+    ok_row = (n == 1 or s1 == 1) and (nf == 1 or s0 >= n) and a.strides[0] % es == 0
+    ok_col = (nf == 1 or s0 == 1) and (n == 1 or s1 >= nf) and a.strides[1] % es == 0 and not ok_row
+    if not (ok_row or ok_col):
+        a = np.ascontiguousarray(a)
+        s0, s1, ok_row = n, 1, True
+    if ok_row:
+        s0, s1 = (s0 if nf > 1 else n), 1
+    else:
+        s0, s1 = 1, (s1 if n > 1 else nf)
+    if out is None:
+        out = np.empty((nf, N_FEATURES), dtype=np.float64)
+    elif out.dtype != np.float64 or out.shape != (nf, N_FEATURES) or not out.flags.c_contiguous:
+        raise ValueError("out must be C-contiguous float64 (n_frames, 18)")
+    rc = nat.lib().amc_extract_host(
+        a.ctypes.data, code, nf, n, s0, s1, out.ctypes.data, N_FEATURES, nat.AMC_ALL_FEATURES,
+        nat.AMC_FLAG_FORCE_GENERAL if force_general else 0, device,
+    )
+    nat.check(rc)
+    return out
+
+
+def frames_from_sample_major(src, n_frames: int, frame_size: int, sample_stride: int, stream=None):
+    """Device re-layout of a flat sample-major block (element (f, n) at f + n*sample_stride) into
+    a (n_frames, frame_size) C-contiguous tensor."""
+    torch = _torch()
+    dst = torch.empty((n_frames, frame_size), dtype=src.dtype, device=src.device)
+    with torch.cuda.device(src.device):
+        rc = nat.lib().amc_frames_from_sample_major(
+            src.data_ptr(), _dtype_code(src), n_frames, frame_size, sample_stride, dst.data_ptr(), _stream_ptr(stream)
+        )
+    nat.check(rc)
+    return dst
+
+
+def instantaneous_batch(iq, stream=None):
+    """dict of float64 CUDA tensors: abs, phase, unwrapped_phase, cn_amplitude (frames, N) and
+    frequency (frames, N-1) - the arrays of the reference's InstantaneousValues (features.py:27-31)."""
+    torch = _torch()
+    x = _as_frames_2d(iq)
+    nf, n = x.shape
+    mk = lambda m: torch.empty((nf, m), dtype=torch.float64, device=x.device)  # noqa: E731
+    res = {"abs": mk(n), "phase": mk(n), "unwrapped_phase": mk(n), "frequency": mk(max(n - 1, 0)), "cn_amplitude": mk(n)}
+    with torch.cuda.device(x.device):
+        rc = nat.lib().amc_instantaneous_batch(
+            x.data_ptr(), _dtype_code(x), nf, n, x.stride(0) if nf > 1 else n, x.stride(1) if n > 1 else 1,
+            res["abs"].data_ptr(), res["phase"].data_ptr(), res["unwrapped_phase"].data_ptr(),
+            res["frequency"].data_ptr() if n > 1 else None, res["cn_amplitude"].data_ptr(), _stream_ptr(stream),
+        )
+    nat.check(rc)
+    return res
+
+
+def moments_batch(iq, stream=None):
+    """complex128 CUDA tensor (frames, 11): m20 m21 m22 m40 m41 m42 m43 m60 m61 m62 m63
+    (features.py:46-58; m21, m42, m62 carry a zero imaginary part)."""
+    torch = _torch()
+    x = _as_frames_2d(iq)
+    nf, n = x.shape
+    out = torch.empty((nf, 22), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = nat.lib().amc_moments_batch(
+            x.data_ptr(), _dtype_code(x), nf, n, x.stride(0) if nf > 1 else n, x.stride(1) if n > 1 else 1,
+            out.data_ptr(), _stream_ptr(stream),
+        )
+    nat.check(rc)
+    return torch.view_as_complex(out.view(nf, 11, 2))

@@ -1,0 +1,131 @@
+/*
+ * amcpy_b200 - C ABI of the B200-native feature-extraction hot path of amcpy.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, no exceptions
+ * across the ABI.  Every entry returns AMC_OK (0) or a negative AMC_ERR_* code and records a
+ * message retrievable (per thread) with amc_last_error_string().
+ *
+ * What each entry replaces in the reference (paths relative to /root/reference/src/amcpy/):
+ *
+ *   amc_extract_batch / amc_extract_host
+ *       the per-frame operator fan-out: `_Worker.run` calling
+ *       `calculate_features(list(range(1, 19)), signal)` for every (snr, frame)
+ *       (feature_extraction.py:30-39, :64-74) and, inside it, the 18 functions of
+ *       features.py:66-185 dispatched through `_FEATURE_FUNCTIONS` (features.py:192-232).
+ *       Output row k of a frame = feature id k+1, float64 (the reference's Python floats);
+ *       the float32 cast of feature_extraction.py:56 is done by the caller that writes .mat.
+ *   amc_instantaneous_batch
+ *       `InstantaneousValues.__init__` (features.py:17-31): abs, phase, unwrapped_phase,
+ *       frequency (N-1 values), cn_amplitude.
+ *   amc_moments_batch
+ *       `MomentValues.__init__` (features.py:39-58): m20 m21 m22 m40 m41 m42 m43 m60 m61 m62 m63.
+ *   amc_frames_from_sample_major
+ *       the strided `parsed[snr, frame, 0:frame_size]` views of a Fortran-ordered loadmat array
+ *       (feature_extraction.py:48,68): turns sample-major storage into one contiguous row per frame.
+ *
+ * Layout contract: a "frame" is `frame_size` complex samples; frame f starts at element
+ * f*frame_stride, sample n of it is at +n*sample_stride (strides in complex ELEMENTS).
+ * The fused sm_100a kernel runs when sample_stride == 1, frame_size is one of
+ * {256, 512, 1024, 2048, 4096} and every frame start is 16-byte aligned; every other shape
+ * (any length >= 1, any strides) runs the general kernel.  Both run on the GPU; there is no CPU path.
+ *
+ * Precision classes vs the reference on complex128 input (tests/ hold the tolerances):
+ *   relative 1e-9 : features 4, 6, 7, 8 and 10..18 (float64 accumulation)
+ *   relative 1e-6 : features 1, 2, 3, 5, 9 (float32 FFT / atan2 in the fused kernel; unwrap branch
+ *                   decisions within 4e-6 rad of +-pi are re-decided in float64 exactly as np.unwrap)
+ *   AMC_FLAG_FORCE_GENERAL computes everything except the power-of-two FFT in float64.
+ */
+#ifndef AMCPY_B200_H
+#define AMCPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMC_N_FEATURES 18
+#define AMC_N_MOMENTS 11
+#define AMC_ALL_FEATURES 0x3FFFFu /* bit k = feature id k+1 */
+
+/* iq_dtype */
+#define AMC_C64 0  /* interleaved float32 re,im  */
+#define AMC_C128 1 /* interleaved float64 re,im  */
+
+/* flags */
+#define AMC_FLAG_FORCE_GENERAL 1 /* never take the fused fixed-size kernel */
+
+/* return codes */
+#define AMC_OK 0
+#define AMC_ERR_INVALID_ARG (-1)
+#define AMC_ERR_UNSUPPORTED (-2) /* frame_size outside what the general kernel's FFT supports */
+#define AMC_ERR_CUDA (-3)
+#define AMC_ERR_NO_DEVICE (-4)
+
+/* Library / ABI version (major*1000 + minor). */
+int amc_version(void);
+
+/* Message of the last failing call made by THIS thread ("" if none). Never NULL. */
+const char* amc_last_error_string(void);
+
+/* Number of CUDA devices visible, or AMC_ERR_NO_DEVICE. */
+int amc_device_count(void);
+
+/*
+ * All 18 features of n_frames frames that already live in device memory (current device),
+ * enqueued on `cuda_stream` (a cudaStream_t, may be NULL for the default stream); does not
+ * synchronise, does not allocate.
+ *   iq           device pointer, complex64/complex128 interleaved
+ *   out          device pointer, float64, row f at out + f*out_stride, out_stride >= 18
+ *   feature_mask bit k = feature k+1 wanted; all 18 columns are always written (a cleared bit
+ *                only lets the library skip work in a later revision); must be non-zero
+ * n_frames == 0 is a no-op.
+ */
+int amc_extract_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size,
+                      int64_t frame_stride, int64_t sample_stride, double* out, int64_t out_stride,
+                      uint32_t feature_mask, int flags, void* cuda_stream);
+
+/*
+ * Same computation for HOST buffers on device `device`: frames are copied to the GPU in
+ * chunks on two streams (copy of chunk i+1 overlaps the kernel of chunk i), features are
+ * copied back; returns when `out` is complete.  Pinned host memory gives full PCIe speed.
+ * Accepts sample_stride == 1 (row per frame, any frame_stride >= frame_size) or the
+ * sample-major layout frame_stride == 1 (what loadmat returns; sample_stride >= n_frames),
+ * which is transposed on the device.
+ */
+int amc_extract_host(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size,
+                     int64_t frame_stride, int64_t sample_stride, double* out, int64_t out_stride,
+                     uint32_t feature_mask, int flags, int device);
+
+/*
+ * Device-side re-layout: src holds n_frames frames sample-major (element (f, n) at
+ * f + n*src_sample_stride); dst receives one contiguous row of frame_size samples per frame.
+ */
+int amc_frames_from_sample_major(const void* src, int iq_dtype, int64_t n_frames, int64_t frame_size,
+                                 int64_t src_sample_stride, void* dst, void* cuda_stream);
+
+/*
+ * InstantaneousValues for a batch (device pointers, float64 outputs, row-major):
+ *   abs, phase, unwrapped, cn_amplitude : [n_frames, frame_size];  frequency : [n_frames, frame_size-1]
+ * Any output pointer may be NULL to skip it.  float64 arithmetic, np.unwrap's rules.
+ */
+int amc_instantaneous_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size,
+                            int64_t frame_stride, int64_t sample_stride, double* abs_out,
+                            double* phase_out, double* unwrapped_out, double* frequency_out,
+                            double* cn_amplitude_out, void* cuda_stream);
+
+/*
+ * MomentValues for a batch: out[f][2*i + {0,1}] = {re, im} of moment i in the order
+ * m20 m21 m22 m40 m41 m42 m43 m60 m61 m62 m63 (m21, m42, m62 have im = 0 as in the reference).
+ * out is device float64 [n_frames, 22].
+ */
+int amc_moments_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size,
+                      int64_t frame_stride, int64_t sample_stride, double* out, void* cuda_stream);
+
+/* How many kernels of this library the calling thread has launched so far (for bench accounting). */
+int64_t amc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMCPY_B200_H */
