@@ -1,0 +1,231 @@
+"""GPU: the drop-in boundary - helper value types, layouts/strides/dtypes, the host pipeline,
+the `run_extraction` stage with its .mat output contract, and error behaviour of the C ABI."""
+
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import SNRS, assert_features_close, golden_frames, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    from amcpy_b200 import _native as nat
+
+    nat.require_cuda()
+    return torch
+
+
+# ------------------------------------------------------------------ helper value types
+def test_instantaneous_values_kat(torch_cuda):
+    # features.py:258-271 through the drop-in class, then bit-level vs the reference's arrays
+    from amcpy_b200.features import InstantaneousValues
+    from oracle import amc_oracle as orc
+
+    iv = InstantaneousValues(orc.kat_signal())
+    assert len(iv.abs) == 10 and len(iv.phase) == 10 and len(iv.unwrapped_phase) == 10
+    assert len(iv.frequency) == 9 and len(iv.cn_amplitude) == 10
+    assert np.isclose(iv.abs[1], np.sqrt(2), atol=1e-10)
+    assert np.isclose(iv.cn_amplitude[0], -1.0, atol=1e-10)
+    assert np.isclose(iv.cn_amplitude[-1], 1.0, atol=1e-10)
+    g = load_golden("kat10.npz")
+    for k in ("abs", "phase", "unwrapped_phase", "frequency", "cn_amplitude"):
+        assert np.allclose(getattr(iv, k), g[f"iv_{k}"], rtol=1e-13, atol=1e-14), k
+    # the fixture sits exactly on np.unwrap's +-pi tie: the sign pattern must be the reference's
+    assert np.array_equal(np.sign(iv.frequency), np.sign(g["iv_frequency"]))
+
+
+def test_moment_values_kat(torch_cuda):
+    # features.py:274-280
+    from amcpy_b200.features import MomentValues
+    from oracle import amc_oracle as orc
+
+    m = MomentValues(orc.kat_signal())
+    assert np.isclose(m.m21, 57.0, atol=1e-10)
+    assert np.isclose(m.m42, 6133.2, atol=1e-6)
+    assert np.isclose(m.m63, 782724.0, atol=1e-6)
+    assert isinstance(m.m21, float) and isinstance(m.m20, complex)
+    g = load_golden("kat10.npz")
+    for k in ("m20", "m21", "m22", "m40", "m41", "m42", "m43", "m60", "m61", "m62", "m63"):
+        assert np.isclose(getattr(m, k), complex(g[f"mv_{k}"]), rtol=1e-12, atol=1e-9), k
+
+
+def test_helpers_realistic_frame_and_batch(torch_cuda):
+    from amcpy_b200 import ops, synth
+    from oracle import amc_oracle as orc
+
+    g = load_golden("helpers_n256.npz")
+    x = synth.frame(1, 10.0, 10, 0, 256, int(g["seed"]))
+    xd = torch_cuda.from_numpy(np.stack([x, x[::-1].copy(), x * 1j])).cuda()   # 3 frames
+    iv = ops.instantaneous_batch(xd)
+    for k in ("abs", "phase", "unwrapped_phase", "frequency", "cn_amplitude"):
+        got = iv[k][0].cpu().numpy()
+        assert np.allclose(got, g[f"iv_{k}"], rtol=1e-12, atol=1e-12), k
+    want2 = orc.instantaneous(x * 1j)
+    for k in want2:
+        assert np.allclose(iv[k][2].cpu().numpy(), want2[k], rtol=1e-12, atol=1e-12), k
+    mv = ops.moments_batch(xd).cpu().numpy()
+    for i, k in enumerate(ops.MOMENT_NAMES):
+        assert np.isclose(mv[0, i], complex(g[f"mv_{k}"]), rtol=1e-11, atol=1e-13), k
+
+
+def test_unwrapped_phase_long_frame_scan(torch_cuda):
+    # several 256-sample chunks with carries: unwrapped phase of a noisy rotating tone
+    from amcpy_b200 import ops
+    from oracle import amc_oracle as orc
+
+    rng = np.random.default_rng(5)
+    n = 3000
+    x = np.exp(1j * 2.9 * np.arange(n)) + 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    iv = ops.instantaneous_batch(torch_cuda.from_numpy(x[None, :]).cuda())
+    want = orc.instantaneous(x)
+    assert np.allclose(iv["unwrapped_phase"][0].cpu().numpy(), want["unwrapped_phase"], rtol=1e-12, atol=1e-9)
+    assert np.allclose(iv["frequency"][0].cpu().numpy(), want["frequency"], rtol=0, atol=1e-12)
+
+
+# ------------------------------------------------------------------ layouts, dtypes, strides
+def test_batched_entry_takes_snr_frames_samples_tensor(torch_cuda):
+    from amcpy_b200 import ops
+
+    x, want = golden_frames(2048)
+    xd = torch_cuda.from_numpy(x[2]).cuda()            # (n_snr=4, n_frames=3, 2048) - north_star's entry shape
+    got = ops.extract_features(xd)
+    assert tuple(got.shape) == (4, 3, 18) and got.dtype == torch_cuda.float64
+    assert_features_close(got.cpu().numpy(), want[2])
+
+
+def test_padded_rows_and_noncontiguous_views(torch_cuda):
+    from amcpy_b200 import ops
+
+    x, want = golden_frames(2048)
+    flat = x.reshape(-1, 2048)
+    pad = np.zeros((flat.shape[0], 2048 + 8), dtype=np.complex128)
+    pad[:, :2048] = flat
+    pd = torch_cuda.from_numpy(pad).cuda()
+    assert_features_close(ops.extract_features(pd[:, :2048]).cpu().numpy(), want)      # row stride 2056: fused
+    # sample-major (what loadmat hands out): general kernel in place, or re-laid-out on the device
+    sm = torch_cuda.from_numpy(np.asfortranarray(flat)).cuda()    # torch keeps the column-major strides
+    assert sm.stride() == (1, flat.shape[0])
+    assert_features_close(ops.extract_features(sm).cpu().numpy(), want)
+    rel = ops.frames_from_sample_major(sm.t().contiguous().view(-1), flat.shape[0], 2048, flat.shape[0])
+    assert torch_cuda.equal(rel, torch_cuda.from_numpy(flat).cuda())
+    # every second frame
+    assert_features_close(ops.extract_features(pd[::2, :2048]).cpu().numpy(), want.reshape(-1, 18)[::2])
+
+
+def test_complex64_input(torch_cuda):
+    from amcpy_b200 import ops
+    from oracle import amc_oracle as orc
+
+    x, _ = golden_frames(1024)
+    x64 = x.reshape(-1, 1024).astype(np.complex64)
+    want = orc.features_batch(x64.astype(np.complex128))   # exact widening: same numbers, float64 arithmetic
+    for force in (False, True):
+        got = ops.extract_features(torch_cuda.from_numpy(x64).cuda(), force_general=force).cpu().numpy()
+        assert_features_close(got, want)
+    # and against numpy computing in float32 like the reference does for c64 input (loose: 1e-4)
+    ref32 = orc.features_batch(x64)
+    got = ops.extract_features(torch_cuda.from_numpy(x64).cuda()).cpu().numpy()
+    assert np.allclose(got, ref32, rtol=2e-4, atol=0)
+
+
+def test_host_pipeline_row_major_and_sample_major(torch_cuda):
+    from amcpy_b200 import ops
+
+    x, want = golden_frames(2048)
+    flat = x.reshape(-1, 2048)
+    big = np.concatenate([flat] * 40)                      # 2880 frames: more than one 64 MiB chunk
+    want_big = np.concatenate([want.reshape(-1, 18)] * 40)
+    got = ops.extract_features_host(big)
+    assert_features_close(got, want_big)
+    got_f = ops.extract_features_host(np.asfortranarray(big))
+    assert np.array_equal(got_f, got)                      # re-layout on device, then the same kernel
+    assert_features_close(ops.extract_features_host(flat[:, :1000]), ops.extract_features_host(
+        np.ascontiguousarray(flat[:, :1000])), scale=1e-3)  # padded rows through the general kernel
+
+
+def test_determinism_and_grid_independence(torch_cuda):
+    from amcpy_b200 import ops
+
+    x, _ = golden_frames(2048)
+    xd = torch_cuda.from_numpy(np.concatenate([x.reshape(-1, 2048)] * 10)).cuda()
+    a = ops.extract_features(xd)
+    b = ops.extract_features(xd)
+    assert torch_cuda.equal(a, b)
+    # a frame's result must not depend on how many frames share the launch
+    c = ops.extract_features(xd[:5])
+    assert torch_cuda.equal(a[:5], c)
+    assert torch_cuda.equal(a[:72], a[72:144])
+
+
+# ------------------------------------------------------------------ the stage (.mat in, .mat out)
+def test_run_extraction_matches_reference_mat_files(torch_cuda, tmp_path):
+    import scipy.io
+
+    from amcpy_b200 import synth
+    from amcpy_b200.config import Config, Paths, SignalConfig
+    from amcpy_b200.feature_extraction import run_extraction
+
+    g = load_golden("stage_16x2x2048.npz")
+    cfg = Config(paths=Paths(root=tmp_path), signals=SignalConfig(num_frames=2))
+    cfg.paths.ensure_dirs()
+    data = synth.dataset(SNRS, 2, 2048 + 8, int(g["seed"]))
+    synth.write_all_modulations_mat(cfg.paths.mat_data / cfg.paths.mat_filename, data, cfg.signals.mat_info)
+    run_extraction(cfg)
+    for mod in cfg.signals.modulations_with_noise:
+        m = scipy.io.loadmat(str(cfg.paths.calculated_features / f"{mod}_features.mat"))
+        key = cfg.signals.mat_info[mod]
+        assert m[key].dtype == np.float32 and m[key].shape == (16, 2, 18)
+        assert np.array_equal(m["Modulation"], g[f"{mod}_modulation"])
+        want = g[f"{mod}_matrix"].astype(np.float64)
+        got = m[key].astype(np.float64)
+        # float32 store (feature_extraction.py:56): 1e-6 class features may differ by one more ulp
+        assert np.allclose(got, want, rtol=1.3e-6, atol=0), mod
+        cols_1e9 = [c for c in range(18) if c + 1 not in (1, 2, 3, 5, 9)]
+        assert np.allclose(got[..., cols_1e9], want[..., cols_1e9], rtol=1.2e-7, atol=0), mod
+
+
+def test_run_extraction_fails_loudly_on_short_data(torch_cuda, tmp_path):
+    from amcpy_b200 import synth
+    from amcpy_b200.config import Config, Paths, SignalConfig
+    from amcpy_b200.feature_extraction import run_extraction
+
+    cfg = Config(paths=Paths(root=tmp_path), signals=SignalConfig(num_frames=5))
+    cfg.paths.ensure_dirs()
+    data = synth.dataset(SNRS, 2, 2048, 3)                  # only 2 frames in the file
+    synth.write_all_modulations_mat(cfg.paths.mat_data / cfg.paths.mat_filename, data, cfg.signals.mat_info)
+    with pytest.raises(ValueError):
+        run_extraction(cfg)
+
+
+# ------------------------------------------------------------------ C ABI error behaviour
+def test_c_abi_error_codes(torch_cuda):
+    from amcpy_b200 import _native as nat
+
+    lib = nat.lib()
+    x = torch_cuda.zeros((4, 256), dtype=torch_cuda.complex128, device="cuda")
+    out = torch_cuda.zeros((4, 18), dtype=torch_cuda.float64, device="cuda")
+    args = dict(dt=nat.AMC_C128, nf=4, n=256, fs=256, ss=1, os=18, mask=nat.AMC_ALL_FEATURES)
+
+    def call(**kw):
+        a = {**args, **kw}
+        return lib.amc_extract_batch(x.data_ptr(), a["dt"], a["nf"], a["n"], a["fs"], a["ss"], out.data_ptr(), a["os"],
+                                     a["mask"], 0, None)
+
+    assert call() == 0
+    assert call(nf=0) == 0
+    assert call(dt=7) == -1 and b"iq_dtype" in lib.amc_last_error_string()
+    assert call(n=0) == -1
+    assert call(os=17) == -1
+    assert call(mask=0) == -1
+    assert call(ss=0) == -1
+    assert call(n=1 << 20, fs=1 << 20) == -2          # power of two beyond the general kernel's FFT scratch
+    assert lib.amc_extract_batch(None, nat.AMC_C128, 4, 256, 256, 1, out.data_ptr(), 18, nat.AMC_ALL_FEATURES, 0, None) == -1
+    with pytest.raises(nat.AmcError):
+        nat.check(call(dt=7))
+    torch_cuda.cuda.synchronize()

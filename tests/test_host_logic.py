@@ -1,0 +1,138 @@
+"""CPU: host-side logic - the library loads and exports every symbol of include/amcpy_b200.h,
+config parity with the reference's field names/defaults, layout planning of the stage, the
+synthetic generator, and that no product module routes through the oracle."""
+
+import ast
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    from amcpy_b200 import _native as nat
+
+    nat.build()
+    return nat.lib()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from amcpy_b200 import _native as nat
+
+    header = (ROOT / "include" / "amcpy_b200.h").read_text()
+    declared = set(re.findall(r"\b(amc_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes found in the header"
+    assert declared == set(nat.SIGNATURES), declared ^ set(nat.SIGNATURES)
+    for name in declared:
+        assert getattr(built_lib, name) is not None
+    assert built_lib.amc_version() >= 1000
+    assert built_lib.amc_last_error_string() is not None
+    assert built_lib.amc_launch_count() == 0
+
+
+def test_no_cuda_device_is_an_error_not_a_fallback(built_lib):
+    import torch
+
+    from amcpy_b200 import _native as nat
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    with pytest.raises(nat.AmcError):
+        nat.require_cuda()
+    from amcpy_b200.config import Config, Paths
+    from amcpy_b200.feature_extraction import run_extraction
+
+    with pytest.raises(nat.AmcError):
+        run_extraction(Config(paths=Paths(root=Path("/tmp/amcpy_b200_nonexistent"))))
+
+
+def test_argument_checks_run_without_a_gpu(built_lib):
+    from amcpy_b200 import _native as nat
+
+    # validation happens before any CUDA call, so these are safe on a CPU-only box
+    assert built_lib.amc_extract_batch(None, 5, 1, 16, 16, 1, None, 18, nat.AMC_ALL_FEATURES, 0, None) == -1
+    assert b"iq_dtype" in built_lib.amc_last_error_string()
+    assert built_lib.amc_extract_batch(None, nat.AMC_C128, 0, 16, 16, 1, None, 18, nat.AMC_ALL_FEATURES, 0, None) == 0
+    assert built_lib.amc_extract_batch(None, nat.AMC_C128, 1, 16, 16, 1, None, 18, nat.AMC_ALL_FEATURES, 0, None) == -1
+    assert built_lib.amc_extract_host(None, nat.AMC_C128, -1, 16, 16, 1, None, 18, nat.AMC_ALL_FEATURES, 0, 0) == -1
+
+
+def test_product_never_imports_the_oracle():
+    for py in (ROOT / "amcpy_b200").rglob("*.py"):
+        tree = ast.parse(py.read_text())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n.split(".")[0] == "oracle" for n in names), f"{py} imports the oracle"
+    for cu in (ROOT / "amcpy_b200" / "csrc").iterdir():
+        assert "oracle" not in cu.read_text()
+
+
+def test_config_defaults_match_reference_contract():
+    from amcpy_b200.config import Config
+
+    c = Config()
+    assert c.signals.frame_size == 2048 and c.signals.num_frames == 1000 and c.signals.num_threads == 8
+    assert c.signals.modulations_with_noise == ("BPSK", "QPSK", "8PSK", "16QAM", "64QAM", "WGN")
+    assert list(c.signals.snr_values.values()) == [str(v) for v in range(-10, 21, 2)]
+    assert c.signals.mat_info == {"BPSK": "signal_bpsk", "QPSK": "signal_qpsk", "8PSK": "signal_8psk",
+                                  "16QAM": "signal_qam16", "64QAM": "signal_qam64", "WGN": "signal_noise"}
+    assert c.features.all_features == tuple(range(1, 19)) and c.features.used == (2, 4, 6, 8, 12, 14)
+    assert c.features.names[1] == r"$\gamma_{max}$" and c.features.names[18] == "$C_{63}$"
+    assert c.paths.mat_filename == "all_modulations.mat"
+    assert c.paths.calculated_features.name == "calculated-features" and c.paths.mat_data.name == "mat-data"
+    with pytest.raises(Exception):
+        c.signals.frame_size = 1  # frozen
+
+
+def test_stage_layout_planning_fortran_and_c_order():
+    from amcpy_b200.feature_extraction import _frames_view
+
+    S, F, L = 4, 5, 40
+    base = (np.arange(S * F * L) + 1j * np.arange(S * F * L)).reshape(S, F, L)
+    for arr in (np.asfortranarray(base), np.ascontiguousarray(base)):
+        seen = np.zeros((S, 3), dtype=bool)
+        for view, si, fi in _frames_view(arr, S, 3, 32):
+            assert view.shape[1] == 32
+            for row, s, f in zip(view, si, fi):
+                if f < 3:
+                    assert np.array_equal(row, arr[s, f, :32])
+                    seen[s, f] = True
+        assert seen.all()
+    # loadmat's order is consumed as ONE sample-major block (no host transpose)
+    views = _frames_view(np.asfortranarray(base), S, 3, 32)
+    assert len(views) == 1 and views[0][0].strides == (16, 16 * S * F)
+
+
+def test_synth_recipe_and_shard_independence():
+    from amcpy_b200 import synth
+
+    a = synth.cell(3, 10.0, 10, range(4), 512, seed=9)
+    b = synth.cell(3, 10.0, 10, [2, 3], 512, seed=9)
+    assert np.array_equal(a[2:], b)                       # frames are keyed individually
+    for m, name in enumerate(synth.MODULATIONS[:5]):
+        pts = synth.constellation(name)
+        assert np.isclose(np.mean(np.abs(pts) ** 2), 1.0)
+        x = synth.frame(m, 100.0, 0, 0, 256, seed=1)      # ~noise-free: every sample on the constellation
+        assert np.min(np.abs(x[:, None] - pts[None, :]), axis=1).max() < 1e-3
+    w = synth.cell(5, 0.0, 5, range(8), 4096, seed=2)
+    assert abs(np.mean(np.abs(w) ** 2) - 1.0) < 0.05      # WGN at 0 dB: unit noise power
+
+
+def test_features_module_surface():
+    from amcpy_b200 import features as F
+
+    assert sorted(F._FEATURE_FUNCTIONS) == list(range(1, 19))
+    assert [F._FEATURE_FUNCTIONS[i].__name__ for i in (1, 2, 9, 10, 18)] == [
+        "_gmax", "_std_abs_phase", "_kurtosis_cnf", "_cumulant_20", "_cumulant_63"]
+    assert F._cumulant_42 is F._FEATURE_FUNCTIONS[14]
+    with pytest.raises(KeyError):
+        F.calculate_features([19], np.zeros(4, dtype=complex))   # unknown id: KeyError before any GPU work
+    assert F.calculate_features([], np.zeros(4, dtype=complex)) == []
