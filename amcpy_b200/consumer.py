@@ -1,0 +1,61 @@
+"""Feature-matrix consumer: what reads calculated-features/*.mat next.
+
+Restates the intended semantics of the reference's `preprocess_data`
+(/root/reference/src/amcpy/preprocessing.py:13-75): per modulation and per selected SNR take the
+`FeatureConfig.used` columns (0-based, exactly as graphics.py:46 / preprocessing.py:55 index them),
+stack to (n_samples, n_used) float32, standardise (zero mean / unit population variance, i.e.
+sklearn's StandardScaler), stratified 80/20 split with random_state=42.  The reference's version
+raises ValueError at preprocessing.py:55 (a (6, N) block assigned into an (N, 6) slot - SURVEY.md
+App. B.3); the transpose is fixed here, nothing else is changed.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import scipy.io
+
+from .config import Config
+
+
+class Standardizer:
+    """mean_/scale_ with StandardScaler's conventions (population std, zero variance -> scale 1)."""
+
+    def fit(self, x: np.ndarray) -> "Standardizer":
+        x64 = x.astype(np.float64)
+        self.mean_ = x64.mean(axis=0)
+        var = x64.var(axis=0)
+        self.scale_ = np.where(var > 0, np.sqrt(var), 1.0)
+        return self
+
+    def transform(self, x: np.ndarray) -> np.ndarray:
+        return ((x - self.mean_) / self.scale_).astype(x.dtype if x.dtype.kind == "f" else np.float64)
+
+
+def stack_features(cfg: Config, mode: str = "training", matrices: dict | None = None):
+    """(x float32 (n_samples, n_used), y int64).  `matrices` may hold {MOD: (n_snr, n_frames, 18)}
+    arrays straight from the extraction (skipping the .mat round trip)."""
+    s, t, f = cfg.signals, cfg.training, cfg.features
+    snr_axis = t.training_snr if mode == "training" else t.all_snr
+    cols = list(f.used)
+    xs, ys = [], []
+    for mod_idx, mod in enumerate(s.modulations_with_noise):
+        if matrices is not None:
+            m = np.asarray(matrices[mod])
+        else:
+            m = scipy.io.loadmat(str(cfg.paths.calculated_features / f"{mod}_features.mat"))[s.mat_info[mod]]
+        for snr in snr_axis:
+            xs.append(np.asarray(m[snr, : s.num_frames][:, cols], dtype=np.float32))   # (n_frames, n_used)
+            ys.append(np.full(s.num_frames, s.labels[mod_idx], dtype=np.int64))
+    return np.concatenate(xs), np.concatenate(ys)
+
+
+def load_feature_set(cfg: Config, mode: str = "training", matrices: dict | None = None):
+    """x_train, x_test, y_train, y_test, scaler - the return shape of preprocessing.py:13-75."""
+    from sklearn.model_selection import train_test_split
+
+    x, y = stack_features(cfg, mode, matrices)
+    scaler = Standardizer().fit(x)
+    xs = scaler.transform(x)
+    x_train, x_test, y_train, y_test = train_test_split(
+        xs, y, test_size=cfg.training.test_size, random_state=cfg.training.random_state, stratify=y)
+    return x_train, x_test, y_train, y_test, scaler

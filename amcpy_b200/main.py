@@ -1,0 +1,75 @@
+"""Command line for the extraction path: `python -m amcpy_b200.main {extract,full,synth}`.
+
+Mirrors the reference's console script for the sub-commands that reach the hot path
+(/root/reference/src/amcpy/main.py:31-32 `extract`, :62-63 `full`, dispatch :160-175).  Unlike the
+reference - whose dispatcher passes (cfg, args) to the one-argument `cmd_extract` and raises
+TypeError (main.py:85 vs :175) - `extract` works.  `full` runs the extraction and then the feature
+consumer (column select + standardise + stratified split) so the matrices are proven loadable;
+plotting / classifier training are outside the hot path.
+`synth` writes a synthetic mat-data/all_modulations.mat the reference can consume as well.
+"""
+
+from __future__ import annotations
+
+import argparse
+from pathlib import Path
+
+from .config import Config, Paths, SignalConfig
+from .feature_extraction import run_extraction
+
+
+def _build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(prog="amcpy", description="AMCPy feature extraction on B200")
+    p.add_argument("--root", type=Path, default=None, help="project root (default: current directory)")
+    p.add_argument("--num-frames", type=int, default=None, help="frames per (modulation, SNR) (default 1000)")
+    p.add_argument("--frame-size", type=int, default=None, help="samples per frame (default 2048)")
+    sub = p.add_subparsers(dest="command", required=True)
+    sub.add_parser("extract", help="Extract features from raw .mat data")
+    sub.add_parser("full", help="extract, then load/standardise/split the feature matrices")
+    s = sub.add_parser("synth", help="write a synthetic mat-data/all_modulations.mat")
+    s.add_argument("--seed", type=int, default=2024)
+    return p
+
+
+def _config(args) -> Config:
+    sig = {}
+    if args.num_frames is not None:
+        sig["num_frames"] = args.num_frames
+    if args.frame_size is not None:
+        sig["frame_size"] = args.frame_size
+    return Config(paths=Paths(root=args.root) if args.root else Paths(), signals=SignalConfig(**sig))
+
+
+def cmd_extract(cfg: Config, args=None) -> None:
+    run_extraction(cfg)
+
+
+def cmd_synth(cfg: Config, args) -> None:
+    from . import synth
+
+    cfg.paths.ensure_dirs()
+    snrs = [float(v) for v in cfg.signals.snr_values.values()]
+    data = synth.dataset(snrs, cfg.signals.num_frames, cfg.signals.frame_size, args.seed)
+    out = cfg.paths.mat_data / cfg.paths.mat_filename
+    synth.write_all_modulations_mat(out, data, cfg.signals.mat_info)
+    print(f"wrote {out}: 6 x {data.shape[1]} x {data.shape[2]} x {data.shape[3]} complex128")
+
+
+def cmd_full(cfg: Config, args=None) -> None:
+    from .consumer import load_feature_set
+
+    cmd_extract(cfg)
+    x_train, x_test, y_train, y_test, _ = load_feature_set(cfg, mode="training")
+    print(f"feature set ready: train {tuple(x_train.shape)}, test {tuple(x_test.shape)}, "
+          f"{len(set(y_train.tolist()))} classes")
+
+
+def main(argv=None) -> None:
+    args = _build_parser().parse_args(argv)
+    cfg = _config(args)
+    cfg.paths.ensure_dirs()
+    {"extract": cmd_extract, "full": cmd_full, "synth": cmd_synth}[args.command](cfg, args)
+
+
+if __name__ == "__main__":
+    main()
