@@ -8,6 +8,7 @@
 #include <string>
 
 #include "amc_fused.cuh"
+#include "amc_fused16.cuh"
 #include "amc_general.cuh"
 
 namespace {
@@ -95,9 +96,43 @@ int launch_fused(const void* iq, int64_t n_frames, int64_t frame_stride, double*
   return AMC_OK;
 }
 
+template <int N, typename CT>
+int launch_fused16(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride,
+                   int sms, cudaStream_t stream) {
+  using Cfg = amc::Fused16Cfg<N, CT>;
+  auto kern = amc::fused16_features_kernel<N, CT>;
+  static thread_local int blocks_per_sm[kMaxDevices] = {};
+  int dev = 0;
+  AMC_CUDA(cudaGetDevice(&dev));
+  if (blocks_per_sm[dev] == 0) {
+    AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int occ = 0;
+    AMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::CTA, Cfg::SMEM_BYTES));
+    if (occ < 1) return fail(AMC_ERR_CUDA, "fused16 kernel N=%d does not fit on this device", N);
+    blocks_per_sm[dev] = occ;
+  }
+  const int64_t want = (n_frames + Cfg::G - 1) / Cfg::G;
+  const int64_t cap = static_cast<int64_t>(sms) * blocks_per_sm[dev];
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  kern<<<grid, Cfg::CTA, Cfg::SMEM_BYTES, stream>>>(static_cast<const CT*>(iq), n_frames, frame_stride, out,
+                                                   out_stride);
+  ++t_launches;
+  AMC_CUDA(cudaGetLastError());
+  return AMC_OK;
+}
+
 template <typename CT>
 int dispatch_fused(int64_t n, const void* iq, int64_t n_frames, int64_t frame_stride, double* out,
-                   int64_t out_stride, int sms, cudaStream_t stream) {
+                   int64_t out_stride, int sms, cudaStream_t stream, bool spt8) {
+  if (!spt8) {
+    switch (n) {
+      case 512: return launch_fused16<512, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 1024: return launch_fused16<1024, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 2048: return launch_fused16<2048, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 4096: return launch_fused16<4096, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      default: break;
+    }
+  }
   switch (n) {
     case 256: return launch_fused<256, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
     case 512: return launch_fused<512, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
@@ -235,9 +270,10 @@ int amc_extract_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t fr
   if (fused) {
     rc = ensure_twiddles(di.dev, stream);
     if (rc != AMC_OK) return rc;
+    const bool spt8 = (flags & AMC_FLAG_FUSED_SPT8) != 0;
     if (iq_dtype == AMC_C128)
-      return dispatch_fused<double2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream);
-    return dispatch_fused<float2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream);
+      return dispatch_fused<double2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, spt8);
+    return dispatch_fused<float2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, spt8);
   }
   if (iq_dtype == AMC_C128)
     return launch_general<double2>(iq, n_frames, frame_size, frame_stride, sample_stride, out, out_stride, di.sms,

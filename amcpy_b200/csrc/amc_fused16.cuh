@@ -1,0 +1,366 @@
+// Fused sm_100a kernel, 16 samples per thread (frame sizes 512..4096).
+//
+// Same algorithm and numerics as amc_fused.cuh, re-shaped around what the B200 pipe measurements
+// (profiles/r1_pipe_microbench.txt) say is scarce - instruction dispatch and the MIO pipe
+// (shuffles, shared-memory wavefronts), not HBM:
+//   * N/16 threads per frame (N=2048: 128 threads = one CTA, three CTAs per SM): every per-thread
+//     fixed cost (cross-lane reductions, partial stores, barriers, edge handling) is paid once per
+//     16 samples instead of once per 8;
+//   * FFT as radix 16 x 16 x (N/256): stage 1 straight from the registers of pass 1, only TWO
+//     shared-memory exchanges (was three), all exchange addresses are base + immediate after an
+//     XOR swizzle of the low four index bits;
+//   * the edge phase (first sample after each warp's run of 32) travels through 64 bytes of shared
+//     memory instead of one shuffle per sample;
+//   * the 18-feature finalisation is batched: warp 0 parks each frame's 25 totals in shared memory
+//     and finalises 16 frames at once, one lane per frame, instead of 32 redundant lanes per frame.
+#pragma once
+#include "amc_fused.cuh"
+
+namespace amc {
+
+__device__ __forceinline__ constexpr int bitrev4(int r) {
+  return ((r & 1) << 3) | ((r & 2) << 1) | ((r & 4) >> 1) | ((r & 8) >> 3);
+}
+
+// 16-point forward DFT in registers (4 x 4 Cooley-Tukey); X_r is left in v[bitrev4(r)].
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+  constexpr float h = 0.70710678118654752440f;
+  constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+  // now Y[k1][n2]: k1=0 -> v[n2], k1=2 -> v[4+n2], k1=1 -> v[8+n2], k1=3 -> v[12+n2]; twiddle W16^(n2*k1)
+  v[9] = c_mul(v[9], make_float2(c1, -s1));                                  // W16^1
+  v[10] = make_float2((v[10].x + v[10].y) * h, (v[10].y - v[10].x) * h);     // W16^2
+  v[11] = c_mul(v[11], make_float2(s1, -c1));                                // W16^3
+  v[5] = make_float2((v[5].x + v[5].y) * h, (v[5].y - v[5].x) * h);          // W16^2
+  v[6] = c_mul_mj(v[6]);                                                     // W16^4
+  v[7] = make_float2((v[7].y - v[7].x) * h, -(v[7].x + v[7].y) * h);         // W16^6
+  v[13] = c_mul(v[13], make_float2(s1, -c1));                                // W16^3
+  v[14] = make_float2((v[14].y - v[14].x) * h, -(v[14].x + v[14].y) * h);    // W16^6
+  v[15] = c_mul(v[15], make_float2(-c1, s1));                                // W16^9
+  dft4(v[0], v[1], v[2], v[3]);
+  dft4(v[8], v[9], v[10], v[11]);
+  dft4(v[4], v[5], v[6], v[7]);
+  dft4(v[12], v[13], v[14], v[15]);
+}
+
+// conflict-free exchange layout for the 16 x 16 x R Stockham passes: low 4 bits ^= bits 4..7
+__device__ __forceinline__ int swz16(int e) { return e ^ ((e >> 4) & 15); }
+
+constexpr int kBatch = 16;        // frames finalised together (one lane each)
+constexpr int kPendStride = 33;   // doubles per parked frame (32 + 1 pad: conflict-free lane-per-frame reads)
+
+template <int N, typename CT>
+struct Fused16Cfg {
+  static constexpr int SPT = 16;
+  static constexpr int GROUP = N / SPT;                  // threads per frame: 32..256
+  static constexpr int CTA = GROUP < 128 ? 128 : GROUP;
+  static constexpr int G = CTA / GROUP;
+  static constexpr int W = GROUP / 32;
+  static constexpr int STAGES = 2;
+  static constexpr int SLOT_BYTES = N * static_cast<int>(sizeof(CT));
+  static constexpr bool C128 = sizeof(CT) == 16;
+  static constexpr int FFTB_BYTES = C128 ? 0 : N * 8;
+  static constexpr int PART_D = 20, PART_F = 12;
+  static constexpr int PART_BYTES = PART_D * 8 + PART_F * 4;            // 208 per (parity, warp)
+  static constexpr int EDGE_BYTES = W * 16 * 4;
+  static constexpr int PEND_BYTES = 2 * kBatch * kPendStride * 8;       // 8448
+  static constexpr int GROUP_BYTES = STAGES * SLOT_BYTES + FFTB_BYTES + 2 * W * PART_BYTES + EDGE_BYTES + PEND_BYTES + 64;
+  static constexpr int SMEM_BYTES = G * GROUP_BYTES;
+  static constexpr int MIN_BLOCKS = (SMEM_BYTES <= 75 * 1024) ? 3 : ((SMEM_BYTES <= 113 * 1024) ? 2 : 1);
+  static constexpr int R3 = N / 256;                     // radix of the last FFT stage: 2, 4, 8, 16
+  static_assert(N >= 512 && N <= 4096 && GROUP % 32 == 0, "frame size outside the 16-samples-per-thread kernel");
+  static_assert(GROUP_BYTES % 16 == 0, "group region must keep 16-byte alignment");
+};
+
+template <int N, typename CT>
+__global__ void __launch_bounds__(Fused16Cfg<N, CT>::CTA, Fused16Cfg<N, CT>::MIN_BLOCKS)
+fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame_stride,
+                        double* __restrict__ out, int64_t out_stride) {
+  using Cfg = Fused16Cfg<N, CT>;
+  constexpr int GROUP = Cfg::GROUP, W = Cfg::W, SPT = Cfg::SPT, R3 = Cfg::R3;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+
+  const int tid = threadIdx.x;
+  const int g = tid / GROUP;
+  const int t = tid % GROUP;
+  const int wg = t >> 5;
+  const int lane = tid & 31;
+
+  unsigned char* gbase = smem_raw + static_cast<size_t>(g) * Cfg::GROUP_BYTES;
+  unsigned char* slots = gbase;
+  float2* fft_b_extra = reinterpret_cast<float2*>(gbase + Cfg::STAGES * Cfg::SLOT_BYTES);
+  unsigned char* part_base = gbase + Cfg::STAGES * Cfg::SLOT_BYTES + Cfg::FFTB_BYTES;
+  float* edge_s = reinterpret_cast<float*>(part_base + 2 * W * Cfg::PART_BYTES) + wg * 16;
+  double* pend = reinterpret_cast<double*>(part_base + 2 * W * Cfg::PART_BYTES + Cfg::EDGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part_base + 2 * W * Cfg::PART_BYTES + Cfg::EDGE_BYTES + Cfg::PEND_BYTES);
+
+  const int64_t gg = static_cast<int64_t>(blockIdx.x) * Cfg::G + g;
+  const int64_t tg = static_cast<int64_t>(gridDim.x) * Cfg::G;
+  const uint64_t policy = l2_evict_first_policy();
+
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < Cfg::STAGES; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      const int64_t f = gg + s * tg;
+      if (f < n_frames) {
+        mbar_arrive_expect_tx(&bars[s], Cfg::SLOT_BYTES);
+        bulk_copy_g2s(slots + s * Cfg::SLOT_BYTES, iq + f * frame_stride, Cfg::SLOT_BYTES, &bars[s], policy);
+      }
+    }
+  }
+
+  // loop-invariant exchange offsets (float2 units)
+  const int tx = t & 15;
+  const int u0 = t ^ ((t >> 4) & 15);                 // swizzled position of element t (+ multiples of GROUP)
+  const int w2base = (t >> 4) * 256;                  // stage-2 output block of this thread
+
+  // frames this group will process in total (for the batched finalisation)
+  const int my_frames = (gg < n_frames) ? static_cast<int>((n_frames - gg + tg - 1) / tg) : 0;
+
+  for (int it = 0; it < my_frames; ++it) {
+    const int64_t f = gg + static_cast<int64_t>(it) * tg;
+    const int slot = it & 1;
+    const uint32_t parity = (it >> 1) & 1;
+    unsigned char* slot_ptr = slots + slot * Cfg::SLOT_BYTES;
+    const CT* xs = reinterpret_cast<const CT*>(slot_ptr);
+    auto part_d = [&](int w) { return reinterpret_cast<double*>(part_base + (slot * W + w) * Cfg::PART_BYTES); };
+    auto part_f = [&](int w) {
+      return reinterpret_cast<float*>(part_base + (slot * W + w) * Cfg::PART_BYTES + Cfg::PART_D * 8);
+    };
+
+    mbar_wait(&bars[slot], parity);
+
+    // ---------------------------------------------------------------- pass 1
+    Monomials mono;
+    mono.clear();
+    double sum_r = 0.0;
+    double r[SPT];
+    float ph[SPT], xr[SPT], xi[SPT];
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      double a, b;
+      load_sample<CT>(xs + t + GROUP * j, a, b, xr[j], xi[j]);
+      const double s = mono.add(a, b);
+      r[j] = sqrt_nr(s);
+      sum_r += r[j];
+      ph[j] = atan2_fast(xi[j], xr[j]);
+    }
+    // phase of the sample after this warp's run of 32, for every j: lane j evaluates it, lane 31 uses it
+    if (lane < SPT) {
+      const int idx = 32 * (wg + 1) + GROUP * lane;
+      float pe = 0.0f;
+      if (idx < N) {
+        double a, b;
+        float af, bf;
+        load_sample<CT>(xs + idx, a, b, af, bf);
+        pe = atan2_fast(bf, af);
+      }
+      edge_s[lane] = pe;
+    }
+    __syncwarp();
+    float fq[SPT];
+    float s_ph = 0.0f, s_aph = 0.0f, s_f = 0.0f;
+    float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      float nb = __shfl_down_sync(0xffffffffu, ph[j], 1);
+      if ((j & 3) == 0) e4 = reinterpret_cast<const float4*>(edge_s)[j >> 2];   // uniform address: broadcast
+      const float ej = (j & 3) == 0 ? e4.x : ((j & 3) == 1 ? e4.y : ((j & 3) == 2 ? e4.z : e4.w));
+      if (lane == 31) nb = ej;
+      const int n = t + GROUP * j;
+      float dd = nb - ph[j];
+      const float add = fabsf(dd);
+      float fj;
+      if (fabsf(add - kPiF) < kTieEps && n + 1 < N) {
+        fj = exact_freq_step<CT>(xs, n);
+      } else {
+        if (add > kPiF) dd -= copysignf(kTwoPiF, dd);
+        fj = dd * kInvTwoPiF;
+      }
+      if (j == SPT - 1 && t == GROUP - 1) fj = 0.0f;   // sample N-1 has no successor
+      fq[j] = fj;
+      s_f += fj;
+      s_ph += ph[j];
+      s_aph += fabsf(ph[j]);
+    }
+    {
+      double acc[16];
+#pragma unroll
+      for (int i = 0; i < 15; ++i) acc[i] = mono.s[i];
+      acc[15] = sum_r;
+      warp_sum_multi<double, 16>(acc, lane);
+      float accf[4] = {s_ph, s_aph, s_f, 0.0f};
+      warp_sum_multi<float, 4>(accf, lane);
+      if ((lane & 1) == 0) part_d(wg)[lane >> 1] = acc[0];
+      if ((lane & 7) == 0) part_f(wg)[lane >> 3] = accf[0];
+    }
+
+    group_sync<GROUP, Cfg::CTA>(g);   // (1) pass-1 partials visible; the slot has been fully read
+
+    double tot_r = 0.0;
+    float tot_ph = 0.0f, tot_aph = 0.0f, tot_f = 0.0f;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      tot_r += part_d(w)[15];
+      tot_ph += part_f(w)[0];
+      tot_aph += part_f(w)[1];
+      tot_f += part_f(w)[2];
+    }
+    const double mu_r = tot_r * (1.0 / N);
+    const float mu_ph = tot_ph * (1.0f / N), mu_aph = tot_aph * (1.0f / N);
+    const float mu_f = tot_f * (1.0f / (N - 1));
+
+    // ---------------------------------------------------------------- pass 2 (registers only)
+    {
+      double c2acc[4] = {0.0, 0.0, 0.0, 0.0};
+      float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) {
+        const double d = r[j] - mu_r;
+        const double d2 = d * d;
+        c2acc[0] += fabs(d);
+        c2acc[1] += d2;
+        c2acc[2] = fma(d2, d2, c2acc[2]);
+        const float e = ph[j] - mu_ph;
+        q2acc[0] = fmaf(e, e, q2acc[0]);
+        const float ea = fabsf(ph[j]) - mu_aph;
+        q2acc[1] = fmaf(ea, ea, q2acc[1]);
+        const float ef = fq[j] - mu_f;
+        const float ef2 = (j == SPT - 1 && t == GROUP - 1) ? 0.0f : ef * ef;
+        q2acc[2] += ef2;
+        q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
+      }
+      warp_sum_multi<double, 4>(c2acc, lane);
+      warp_sum_multi<float, 4>(q2acc, lane);
+      if ((lane & 7) == 0) {
+        part_d(wg)[16 + (lane >> 3)] = c2acc[0];
+        part_f(wg)[4 + (lane >> 3)] = q2acc[0];
+      }
+    }
+
+    // ---------------------------------------------------------------- spectral max: 16 x 16 x R3 FFT
+    float2* buf_a = reinterpret_cast<float2*>(slot_ptr);
+    float2* buf_b = Cfg::C128 ? reinterpret_cast<float2*>(slot_ptr + N * 8) : fft_b_extra;
+    float vmax = 0.0f;
+    {
+      float2 v[16];
+      // stage 1 (Ns = 1): inputs are this thread's 16 samples t + (N/16) q
+#pragma unroll
+      for (int q = 0; q < 16; ++q) v[q] = make_float2(xr[q], xi[q]);
+      dft16(v);
+      {
+        float2* row = buf_a + 16 * t;                       // element 16 t + q -> position q ^ (t & 15)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) row[q ^ tx] = v[bitrev4(q)];
+      }
+      group_sync<GROUP, Cfg::CTA>(g);   // (2)
+
+      // stage 2 (Ns = 16): element t + GROUP q ; (e >> 4) & 15 = (t >> 4) + (GROUP/16) q  (no carry)
+#pragma unroll
+      for (int q = 0; q < 16; ++q) v[q] = buf_a[(u0 ^ (((GROUP / 16) * q) & 15)) + GROUP * q];
+      {
+        const float2* twk = g_twiddle + tx * (kTwN / 256);  // W_256^(tx q) = table[tx q 16]
+#pragma unroll
+        for (int q = 1; q < 16; ++q) v[q] = c_mul(v[q], twk[tx * (kTwN / 256) * (q - 1)]);
+      }
+      dft16(v);
+      {
+        // element 256 (t>>4) + 16 q + tx  ->  (e >> 4) & 15 = q
+        float2* blk = buf_b + w2base;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) blk[16 * q + (tx ^ q)] = v[bitrev4(q)];
+      }
+      group_sync<GROUP, Cfg::CTA>(g);   // (3)
+
+      // stage 3 (Ns = 256, last): radix R3, 256 butterflies per frame, 16/R3 per thread
+#pragma unroll
+      for (int bb = 0; bb < 16 / R3; ++bb) {
+        const int jj = t + GROUP * bb;                      // 0..255
+        const int p0 = jj ^ ((jj >> 4) & 15);               // (e >> 4) & 15 = (jj >> 4) & 15 for e = jj + 256 q
+        float2 u[R3];
+#pragma unroll
+        for (int q = 0; q < R3; ++q) u[q] = buf_b[p0 + 256 * q];
+        const float2* twj = g_twiddle + jj * (kTwN / N);    // W_N^(jj q) = table[jj q 4096/N]
+#pragma unroll
+        for (int q = 1; q < R3; ++q) u[q] = c_mul(u[q], twj[jj * (kTwN / N) * (q - 1)]);
+        if constexpr (R3 == 2) {
+          bfly2(u[0], u[1]);
+        } else if constexpr (R3 == 4) {
+          dft4(u[0], u[1], u[2], u[3]);
+        } else if constexpr (R3 == 8) {
+          float2(&u8)[8] = reinterpret_cast<float2(&)[8]>(u);
+          dft8(u8);
+        } else {
+          float2(&u16)[16] = reinterpret_cast<float2(&)[16]>(u);
+          dft16(u16);
+        }
+#pragma unroll
+        for (int q = 0; q < R3; ++q) vmax = fmaxf(vmax, fmaf(u[q].x, u[q].x, u[q].y * u[q].y));
+      }
+    }
+    vmax = warp_max(vmax);
+    if (lane == 0) part_f(wg)[8] = vmax;
+
+    group_sync<GROUP, Cfg::CTA>(g);   // (4) all partials of this frame are in shared memory; slot free
+
+    if (t == 0) {
+      const int64_t fn = f + Cfg::STAGES * tg;
+      if (fn < n_frames) {
+        fence_proxy_async_smem();
+        mbar_arrive_expect_tx(&bars[slot], Cfg::SLOT_BYTES);
+        bulk_copy_g2s(slot_ptr, iq + fn * frame_stride, Cfg::SLOT_BYTES, &bars[slot], policy);
+      }
+    }
+    if (wg == 0) {
+      // park this frame's totals: lane i owns value i of the 25
+      const int bi = it % kBatch, half = (it / kBatch) & 1;
+      double* pe = pend + (half * kBatch + bi) * kPendStride;
+      if (lane < 19) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) s += part_d(w)[lane];
+        pe[lane] = s;
+      } else if (lane < 25) {
+        // 19..22 <- float sums 4..7 ; 23 <- sum f (float 2) ; 24 <- spectral max (float 8)
+        const int src = (lane < 23) ? (lane - 15) : (lane == 23 ? 2 : 8);
+        float s = part_f(0)[src];
+#pragma unroll
+        for (int w = 1; w < W; ++w) s = (lane == 24) ? fmaxf(s, part_f(w)[src]) : s + part_f(w)[src];
+        pe[lane] = static_cast<double>(s);
+      }
+      const bool last = (it == my_frames - 1);
+      if (bi == kBatch - 1 || last) {
+        __syncwarp();
+        const int cnt = bi + 1;
+        if (lane < cnt) {
+          const double* pl = pend + (half * kBatch + lane) * kPendStride;
+          FrameSums fs;
+#pragma unroll
+          for (int i = 0; i < 15; ++i) fs.mono[i] = pl[i];
+          fs.sum_r = pl[15];
+          fs.c_abs1 = pl[16];
+          fs.c2 = pl[17];
+          fs.c4 = pl[18];
+          fs.ph_m2 = pl[19];
+          fs.aph_m2 = pl[20];
+          fs.f_m2 = pl[21];
+          fs.f_m4 = pl[22];
+          fs.mean_f = pl[23] / (N - 1);
+          fs.spec_max = pl[24];
+          const int64_t fo = gg + static_cast<int64_t>(it - bi + lane) * tg;
+          finalize_features(fs, N, out + fo * out_stride);
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+}  // namespace amc
