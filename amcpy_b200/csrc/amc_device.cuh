@@ -118,39 +118,42 @@ __device__ __forceinline__ double unwrap_step(double dd) {
 }
 
 // ------------------------------------------------------------------ float32 atan2 (1e-6 class)
-// atan(q) on [0,1] = q + q*s*P(s), s = q*q, degree-7 P fitted minimax (abs err 7e-9 before rounding).
+// atan(q) on [0,1] = q + q*s*P(s), s = q*q, degree-6 P fitted minimax (abs err 5e-8 before rounding).
+// Predicate-free octant / quadrant fix-ups (FSET.BF + sign-bit masks) so that many evaluations can
+// be interleaved without spilling predicates.  atan2(+-0, +-0) follows IEEE / np.angle.
 __device__ __forceinline__ float atan2_fast(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
-  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float mx = fmaxf(fmaxf(ax, ay), 1.0e-37f), mn = fminf(ax, ay);
   float rc;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
-  float q = mn * rc;
-  q = fmaf(fmaf(-q, mx, mn), rc, q);  // one Newton step: q = mn/mx to ~0.5 ulp
-  if (!(mx > 0.0f) || !(mx < 3.0e38f)) q = (mx > 0.0f && ay == ax) ? 1.0f : 0.0f;  // 0/0, inf
+  const float q = mn * rc;
   const float s = q * q;
-  float p = 0.0026222222950309515f;
-  p = fmaf(p, s, -0.015132443979382515f);
-  p = fmaf(p, s, 0.0411217026412487f);
-  p = fmaf(p, s, -0.07366692274808884f);
-  p = fmaf(p, s, 0.10573925077915192f);
-  p = fmaf(p, s, -0.1418597400188446f);
-  p = fmaf(p, s, 0.1999039649963379f);
-  p = fmaf(p, s, -0.33332985639572144f);
-  float r = fmaf(q * s, p, q);
-  if (ay > ax) r = kPiO2F - r;
-  if (__float_as_int(x) < 0) r = kPiF - r;  // sign bit, so x = -0 behaves like atan2
-  return copysignf(r, y);
+  float p = -0.004355369135737419f;
+  p = fmaf(p, s, 0.023040004074573517f);
+  p = fmaf(p, s, -0.0577734000980854f);
+  p = fmaf(p, s, 0.09794221073389053f);
+  p = fmaf(p, s, -0.13976576924324036f);
+  p = fmaf(p, s, 0.19962702691555023f);
+  p = fmaf(p, s, -0.3333165943622589f);
+  float r = fmaf(q * s, p, q);                              // [0, pi/4]
+  const float swap = (ay > ax) ? 1.0f : 0.0f;               // FSET.BF
+  r = fabsf(fmaf(swap, -kPiO2F, r));                        // ay > ax: pi/2 - r
+  const int neg = __float_as_int(x) >> 31;                  // all ones when the sign bit of x is set
+  r = fabsf(r - __int_as_float(neg & __float_as_int(kPiF)));  // x < 0 (or -0): pi - r
+  return __int_as_float((__float_as_int(r) & 0x7fffffff) | (__float_as_int(y) & 0x80000000));
 }
 
 // ------------------------------------------------------------------ |x| in float64 without DSQRT
 // r = sqrt(s) from MUFU.RSQ64H (rsqrt.approx.f64, ~2^-22) + one coupled Newton step (rel err ~1e-13).
+// The seed's input is clamped and halved with integer ops on the high word (s == 0 -> r == 0).
 __device__ __forceinline__ double sqrt_nr(double s) {
+  const int hi = max(__double2hiint(s), 0x00200000);        // >= 2^-1021: rsqrt stays finite, NaN stays NaN
   double y;
-  const double sc = fmax(s, 1.0e-290);
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(sc));
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(__hiloint2double(hi, 0)));
+  // note: for normal s the seed ignores the low word anyway (MUFU.RSQ64H reads the high word only)
+  const double yh = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));   // y / 2
   const double r0 = s * y;
-  const double h = 0.5 * y;
-  const double e = fma(-r0, h, 0.5);
+  const double e = fma(-r0, yh, 0.5);
   return fma(r0, e, r0);
 }
 
@@ -162,6 +165,27 @@ struct Monomials {
   __device__ __forceinline__ void clear() {
 #pragma unroll
     for (int i = 0; i < 15; ++i) s[i] = 0.0;
+  }
+  // first sample: plain stores instead of 15 accumulations onto zero; returns a*a + b*b
+  __device__ __forceinline__ double init(double a, double b) {
+    const double a2 = a * a, b2 = b * b, ab = a * b;
+    s[0] = a2;
+    s[1] = b2;
+    s[2] = ab;
+    const double a4 = a2 * a2, b4 = b2 * b2, a2b2 = a2 * b2;
+    s[3] = a4;
+    s[4] = a2 * ab;
+    s[5] = a2b2;
+    s[6] = ab * b2;
+    s[7] = b4;
+    s[8] = a4 * a2;
+    s[9] = a4 * ab;
+    s[10] = a4 * b2;
+    s[11] = a2b2 * ab;
+    s[12] = b4 * a2;
+    s[13] = b4 * ab;
+    s[14] = b4 * b2;
+    return a2 + b2;
   }
   // returns a*a + b*b
   __device__ __forceinline__ double add(double a, double b) {
@@ -238,7 +262,7 @@ struct FrameSums {
 };
 
 // Writes the 18 features (column k = feature id k+1, features.py:192-211).
-__device__ __forceinline__ void finalize_features(const FrameSums& fs, int n, double* __restrict__ out) {
+__device__ __noinline__ void finalize_features(const FrameSums& fs, int n, double* __restrict__ out) {
   const double dn = static_cast<double>(n);
   const double inv_n = 1.0 / dn;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);

@@ -139,17 +139,16 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
 
     // ---------------------------------------------------------------- pass 1
     Monomials mono;
-    mono.clear();
-    double sum_r = 0.0;
+    double sum_r;
     double r[SPT];
     float ph[SPT], xr[SPT], xi[SPT];
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
       double a, b;
       load_sample<CT>(xs + t + GROUP * j, a, b, xr[j], xi[j]);
-      const double s = mono.add(a, b);
+      const double s = (j == 0) ? mono.init(a, b) : mono.add(a, b);
       r[j] = sqrt_nr(s);
-      sum_r += r[j];
+      sum_r = (j == 0) ? r[j] : sum_r + r[j];
       ph[j] = atan2_fast(xi[j], xr[j]);
     }
     // phase of the sample after this warp's run of 32, for every j: lane j evaluates it, lane 31 uses it
@@ -165,8 +164,12 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       edge_s[lane] = pe;
     }
     __syncwarp();
+    // wrapped phase differences (np.unwrap); differences within kTieEps of +-pi are only flagged
+    // here and re-decided in FP64 after the loop, so the hot loop stays branch-free
     float fq[SPT];
-    float s_ph = 0.0f, s_aph = 0.0f, s_f = 0.0f;
+    float s_ph = 0.0f, s_aph = 0.0f;
+    unsigned tie_mask = 0u;
+    const float last_keep = (t == GROUP - 1) ? 0.0f : 1.0f;   // sample N-1 has no successor
     float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
@@ -174,22 +177,25 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       if ((j & 3) == 0) e4 = reinterpret_cast<const float4*>(edge_s)[j >> 2];   // uniform address: broadcast
       const float ej = (j & 3) == 0 ? e4.x : ((j & 3) == 1 ? e4.y : ((j & 3) == 2 ? e4.z : e4.w));
       if (lane == 31) nb = ej;
-      const int n = t + GROUP * j;
       float dd = nb - ph[j];
-      const float add = fabsf(dd);
-      float fj;
-      if (fabsf(add - kPiF) < kTieEps && n + 1 < N) {
-        fj = exact_freq_step<CT>(xs, n);
-      } else {
-        if (add > kPiF) dd -= copysignf(kTwoPiF, dd);
-        fj = dd * kInvTwoPiF;
-      }
-      if (j == SPT - 1 && t == GROUP - 1) fj = 0.0f;   // sample N-1 has no successor
+      const float over = fabsf(dd) - kPiF;
+      if (fabsf(over) < kTieEps) tie_mask |= 1u << j;
+      if (over > 0.0f) dd -= copysignf(kTwoPiF, dd);
+      float fj = dd * kInvTwoPiF;
+      if (j == SPT - 1) fj *= last_keep;
       fq[j] = fj;
-      s_f += fj;
       s_ph += ph[j];
       s_aph += fabsf(ph[j]);
     }
+    if (t == GROUP - 1) tie_mask &= ~(1u << (SPT - 1));
+    if (tie_mask != 0u) {   // rare (about once per 10^5 samples on noisy data)
+#pragma unroll
+      for (int j = 0; j < SPT; ++j)
+        if (tie_mask & (1u << j)) fq[j] = exact_freq_step<CT>(xs, t + GROUP * j);
+    }
+    float s_f = 0.0f;
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) s_f += fq[j];
     {
       double acc[16];
 #pragma unroll
@@ -232,8 +238,9 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         q2acc[0] = fmaf(e, e, q2acc[0]);
         const float ea = fabsf(ph[j]) - mu_aph;
         q2acc[1] = fmaf(ea, ea, q2acc[1]);
-        const float ef = fq[j] - mu_f;
-        const float ef2 = (j == SPT - 1 && t == GROUP - 1) ? 0.0f : ef * ef;
+        float ef = fq[j] - mu_f;
+        if (j == SPT - 1) ef *= last_keep;
+        const float ef2 = ef * ef;
         q2acc[2] += ef2;
         q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
       }
@@ -260,22 +267,34 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
 #pragma unroll
         for (int q = 0; q < 16; ++q) row[q ^ tx] = v[bitrev4(q)];
       }
+      // twiddles of the next stage are fetched BEFORE the barrier so their latency hides behind it
+      float2 tw2[15];
+      {
+        const float2* twk = g_twiddle + tx * (kTwN / 256);  // W_256^(tx q) = table[tx q 16]
+#pragma unroll
+        for (int q = 1; q < 16; ++q) tw2[q - 1] = twk[tx * (kTwN / 256) * (q - 1)];
+      }
       group_sync<GROUP, Cfg::CTA>(g);   // (2)
 
       // stage 2 (Ns = 16): element t + GROUP q ; (e >> 4) & 15 = (t >> 4) + (GROUP/16) q  (no carry)
 #pragma unroll
       for (int q = 0; q < 16; ++q) v[q] = buf_a[(u0 ^ (((GROUP / 16) * q) & 15)) + GROUP * q];
-      {
-        const float2* twk = g_twiddle + tx * (kTwN / 256);  // W_256^(tx q) = table[tx q 16]
 #pragma unroll
-        for (int q = 1; q < 16; ++q) v[q] = c_mul(v[q], twk[tx * (kTwN / 256) * (q - 1)]);
-      }
+      for (int q = 1; q < 16; ++q) v[q] = c_mul(v[q], tw2[q - 1]);
       dft16(v);
       {
         // element 256 (t>>4) + 16 q + tx  ->  (e >> 4) & 15 = q
         float2* blk = buf_b + w2base;
 #pragma unroll
         for (int q = 0; q < 16; ++q) blk[16 * q + (tx ^ q)] = v[bitrev4(q)];
+      }
+      float2 tw3[(16 / R3) * (R3 - 1)];
+#pragma unroll
+      for (int bb = 0; bb < 16 / R3; ++bb) {
+        const int jj = t + GROUP * bb;
+        const float2* twj = g_twiddle + jj * (kTwN / N);    // W_N^(jj q) = table[jj q 4096/N]
+#pragma unroll
+        for (int q = 1; q < R3; ++q) tw3[bb * (R3 - 1) + q - 1] = twj[jj * (kTwN / N) * (q - 1)];
       }
       group_sync<GROUP, Cfg::CTA>(g);   // (3)
 
@@ -287,9 +306,8 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         float2 u[R3];
 #pragma unroll
         for (int q = 0; q < R3; ++q) u[q] = buf_b[p0 + 256 * q];
-        const float2* twj = g_twiddle + jj * (kTwN / N);    // W_N^(jj q) = table[jj q 4096/N]
 #pragma unroll
-        for (int q = 1; q < R3; ++q) u[q] = c_mul(u[q], twj[jj * (kTwN / N) * (q - 1)]);
+        for (int q = 1; q < R3; ++q) u[q] = c_mul(u[q], tw3[bb * (R3 - 1) + q - 1]);
         if constexpr (R3 == 2) {
           bfly2(u[0], u[1]);
         } else if constexpr (R3 == 4) {
