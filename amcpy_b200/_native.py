@@ -16,7 +16,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "_lib"
-LIB_PATH = LIB_DIR / "libamcpy_b200.so"
+LIB_PATH = Path(os.environ.get("AMCPY_B200_LIB", LIB_DIR / "libamcpy_b200.so"))   # override: A/B builds only
 HEADER = PKG.parent / "include" / "amcpy_b200.h"
 
 AMC_C64, AMC_C128 = 0, 1

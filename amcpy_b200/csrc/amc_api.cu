@@ -62,7 +62,8 @@ int ensure_twiddles(int dev, cudaStream_t stream) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_tw_ready[dev]) return AMC_OK;
   amc::init_twiddle_kernel<<<amc::kTwN / 256, 256, 0, stream>>>();
-  ++t_launches;
+  amc::init_twiddle16_kernel<<<26, 256, 0, stream>>>();
+  t_launches += 2;
   AMC_CUDA(cudaGetLastError());
   AMC_CUDA(cudaStreamSynchronize(stream));  // once per device: later calls on other streams may rely on it
   g_tw_ready[dev] = true;

@@ -140,7 +140,10 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
   r = fabsf(fmaf(swap, -kPiO2F, r));                        // ay > ax: pi/2 - r
   const int neg = __float_as_int(x) >> 31;                  // all ones when the sign bit of x is set
   r = fabsf(r - __int_as_float(neg & __float_as_int(kPiF)));  // x < 0 (or -0): pi - r
-  return __int_as_float((__float_as_int(r) & 0x7fffffff) | (__float_as_int(y) & 0x80000000));
+  // copysign(r, y) as ONE LOP3: (r & ~m) | (y & m), m = sign mask  (LUT 0xD8)
+  unsigned res;
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=r"(res) : "r"(__float_as_uint(r)), "r"(__float_as_uint(y)));
+  return __uint_as_float(res);
 }
 
 // ------------------------------------------------------------------ |x| in float64 without DSQRT

@@ -44,6 +44,38 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
   dft4(v[12], v[13], v[14], v[15]);
 }
 
+// Twiddle tables laid out the way the warps read them (lane-contiguous), so every twiddle load
+// touches one or two 128-byte lines.  (Indexing the generic W_4096 table made each load touch
+// 16-28 lines and the L1TEX pipe - not HBM, not the FP pipes - became the kernel's bottleneck:
+// 32 % of the run time, see profiles/r1_experiments.txt.)
+//   g_tw_s2[q-1][tx]        = W_256^(tx q)          q = 1..15, tx = 0..15
+//   g_tw_s3[off(N)][q-1][j] = W_N^(j q)             q = 1..N/256-1, j = 0..255
+__device__ float2 g_tw_s2[15 * 16];
+__device__ float2 g_tw_s3[(1 + 3 + 7 + 15) * 256];
+__host__ __device__ constexpr int tw_s3_offset(int n) {       // rows before frame size n
+  return (n == 512 ? 0 : (n == 1024 ? 1 : (n == 2048 ? 4 : 11))) * 256;
+}
+__global__ void init_twiddle16_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 15 * 16) {
+    const int q = i / 16 + 1, tx = i % 16;
+    double sn, cs;
+    sincospi(-2.0 * static_cast<double>(tx * q) / 256.0, &sn, &cs);
+    g_tw_s2[i] = make_float2(static_cast<float>(cs), static_cast<float>(sn));
+  }
+  if (i < 26 * 256) {
+    const int row = i / 256, j = i % 256;
+    int n, q;
+    if (row < 1) { n = 512; q = row + 1; }
+    else if (row < 4) { n = 1024; q = row - 1 + 1; }
+    else if (row < 11) { n = 2048; q = row - 4 + 1; }
+    else { n = 4096; q = row - 11 + 1; }
+    double sn, cs;
+    sincospi(-2.0 * static_cast<double>(j * q) / static_cast<double>(n), &sn, &cs);
+    g_tw_s3[i] = make_float2(static_cast<float>(cs), static_cast<float>(sn));
+  }
+}
+
 // conflict-free exchange layout for the 16 x 16 x R Stockham passes: low 4 bits ^= bits 4..7
 __device__ __forceinline__ int swz16(int e) { return e ^ ((e >> 4) & 15); }
 
@@ -146,10 +178,19 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     for (int j = 0; j < SPT; ++j) {
       double a, b;
       load_sample<CT>(xs + t + GROUP * j, a, b, xr[j], xi[j]);
+#ifndef AMC_EXP_NO_FP64
       const double s = (j == 0) ? mono.init(a, b) : mono.add(a, b);
       r[j] = sqrt_nr(s);
+#else
+      if (j == 0) mono.clear();
+      r[j] = a + b;
+#endif
       sum_r = (j == 0) ? r[j] : sum_r + r[j];
+#ifndef AMC_EXP_NO_PHASE
       ph[j] = atan2_fast(xi[j], xr[j]);
+#else
+      ph[j] = xi[j] + xr[j];
+#endif
     }
     // phase of the sample after this warp's run of 32, for every j: lane j evaluates it, lane 31 uses it
     if (lane < SPT) {
@@ -256,6 +297,9 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     float2* buf_a = reinterpret_cast<float2*>(slot_ptr);
     float2* buf_b = Cfg::C128 ? reinterpret_cast<float2*>(slot_ptr + N * 8) : fft_b_extra;
     float vmax = 0.0f;
+#ifdef AMC_EXP_NO_FFT
+    vmax = xr[0] + xi[15];
+#else
     {
       float2 v[16];
       // stage 1 (Ns = 1): inputs are this thread's 16 samples t + (N/16) q
@@ -270,18 +314,25 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       // twiddles of the next stage are fetched BEFORE the barrier so their latency hides behind it
       float2 tw2[15];
       {
-        const float2* twk = g_twiddle + tx * (kTwN / 256);  // W_256^(tx q) = table[tx q 16]
 #pragma unroll
-        for (int q = 1; q < 16; ++q) tw2[q - 1] = twk[tx * (kTwN / 256) * (q - 1)];
+        for (int q = 1; q < 16; ++q) tw2[q - 1] = g_tw_s2[(q - 1) * 16 + tx];   // one 128-byte line per load
       }
+#ifndef AMC_EXP_NO_BAR23
       group_sync<GROUP, Cfg::CTA>(g);   // (2)
+#endif
 
       // stage 2 (Ns = 16): element t + GROUP q ; (e >> 4) & 15 = (t >> 4) + (GROUP/16) q  (no carry)
 #pragma unroll
       for (int q = 0; q < 16; ++q) v[q] = buf_a[(u0 ^ (((GROUP / 16) * q) & 15)) + GROUP * q];
 #pragma unroll
+#ifndef AMC_EXP_NO_TWMUL
       for (int q = 1; q < 16; ++q) v[q] = c_mul(v[q], tw2[q - 1]);
+#else
+      v[1].x += tw2[0].x + tw2[14].y;
+#endif
+#ifndef AMC_EXP_NO_DFT2
       dft16(v);
+#endif
       {
         // element 256 (t>>4) + 16 q + tx  ->  (e >> 4) & 15 = q
         float2* blk = buf_b + w2base;
@@ -292,11 +343,12 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
 #pragma unroll
       for (int bb = 0; bb < 16 / R3; ++bb) {
         const int jj = t + GROUP * bb;
-        const float2* twj = g_twiddle + jj * (kTwN / N);    // W_N^(jj q) = table[jj q 4096/N]
 #pragma unroll
-        for (int q = 1; q < R3; ++q) tw3[bb * (R3 - 1) + q - 1] = twj[jj * (kTwN / N) * (q - 1)];
+        for (int q = 1; q < R3; ++q) tw3[bb * (R3 - 1) + q - 1] = g_tw_s3[tw_s3_offset(N) + (q - 1) * 256 + jj];
       }
+#ifndef AMC_EXP_NO_BAR23
       group_sync<GROUP, Cfg::CTA>(g);   // (3)
+#endif
 
       // stage 3 (Ns = 256, last): radix R3, 256 butterflies per frame, 16/R3 per thread
 #pragma unroll
@@ -307,7 +359,11 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
 #pragma unroll
         for (int q = 0; q < R3; ++q) u[q] = buf_b[p0 + 256 * q];
 #pragma unroll
+#ifndef AMC_EXP_NO_TWMUL
         for (int q = 1; q < R3; ++q) u[q] = c_mul(u[q], tw3[bb * (R3 - 1) + q - 1]);
+#else
+        u[1].x += tw3[bb * (R3 - 1)].x + tw3[bb * (R3 - 1) + R3 - 2].y;
+#endif
         if constexpr (R3 == 2) {
           bfly2(u[0], u[1]);
         } else if constexpr (R3 == 4) {
@@ -323,6 +379,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         for (int q = 0; q < R3; ++q) vmax = fmaxf(vmax, fmaf(u[q].x, u[q].x, u[q].y * u[q].y));
       }
     }
+#endif
     vmax = warp_max(vmax);
     if (lane == 0) part_f(wg)[8] = vmax;
 
