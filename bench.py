@@ -311,7 +311,7 @@ def run_cuda_arm(args):
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "fused_features_kernel<2048,double2>",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "fused16_features_kernel<2048,double2>",
                 "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": n_frames * BYTES_PER_FRAME,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
             },
