@@ -27,6 +27,36 @@ __global__ void init_twiddle_kernel() {
   }
 }
 
+// Lane-contiguous twiddle tables for the 8-samples-per-thread kernel (one or two 128-byte lines
+// per warp load instead of 8-32 with the generic table; see profiles/r1_experiments.txt):
+//   g_tw8_s2[q-1][k]          = W_64^(k q)    q=1..7, k=0..7
+//   g_tw8_s3a[q-1][j]         = W_256^(j q)   q=1..3, j=0..63     (N = 256, last stage)
+//   g_tw8_s3b[q-1][k]         = W_512^(k q)   q=1..7, k=0..63
+//   g_tw8_s4[off(N)+q-1][j]   = W_N^(j q)     q=1..N/512-1, j=0..511
+__device__ float2 g_tw8_s2[7 * 8];
+__device__ float2 g_tw8_s3a[3 * 64];
+__device__ float2 g_tw8_s3b[7 * 64];
+__device__ float2 g_tw8_s4[11 * 512];
+__host__ __device__ constexpr int tw8_s4_offset(int n) { return (n == 1024 ? 0 : (n == 2048 ? 1 : 4)) * 512; }
+
+__device__ __forceinline__ float2 tw_exact(int num, int den) {
+  double s, c;
+  sincospi(-2.0 * static_cast<double>(num) / static_cast<double>(den), &s, &c);
+  return make_float2(static_cast<float>(c), static_cast<float>(s));
+}
+__global__ void init_twiddle8_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 7 * 8) g_tw8_s2[i] = tw_exact((i % 8) * (i / 8 + 1), 64);
+  if (i < 3 * 64) g_tw8_s3a[i] = tw_exact((i % 64) * (i / 64 + 1), 256);
+  if (i < 7 * 64) g_tw8_s3b[i] = tw_exact((i % 64) * (i / 64 + 1), 512);
+  if (i < 11 * 512) {
+    const int row = i / 512, j = i % 512;
+    const int n = row < 1 ? 1024 : (row < 4 ? 2048 : 4096);
+    const int q = row < 1 ? 1 : (row < 4 ? row : row - 3);
+    g_tw8_s4[i] = tw_exact(j * q, n);
+  }
+}
+
 // ------------------------------------------------------------------ small complex FP32 FFT pieces
 __device__ __forceinline__ float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -310,7 +340,7 @@ fused_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = buf_a[swz(t + GROUP * q)];
 #pragma unroll
-        for (int q = 1; q < 8; ++q) v[q] = c_mul(v[q], g_twiddle[k * q * (kTwN / 64)]);
+        for (int q = 1; q < 8; ++q) v[q] = c_mul(v[q], g_tw8_s2[(q - 1) * 8 + k]);
         dft8(v);
         const int base = (t >> 3) * 64 + k;
 #pragma unroll
@@ -327,7 +357,7 @@ fused_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
 #pragma unroll
           for (int q = 0; q < 4; ++q) u[q] = buf_b[swz(jj + 64 * q)];
 #pragma unroll
-          for (int q = 1; q < 4; ++q) u[q] = c_mul(u[q], g_twiddle[jj * q * (kTwN / 256)]);
+          for (int q = 1; q < 4; ++q) u[q] = c_mul(u[q], g_tw8_s3a[(q - 1) * 64 + jj]);
           dft4(u[0], u[1], u[2], u[3]);
 #pragma unroll
           for (int q = 0; q < 4; ++q) vmax = fmaxf(vmax, fmaf(u[q].x, u[q].x, u[q].y * u[q].y));
@@ -338,7 +368,7 @@ fused_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = buf_b[swz(t + GROUP * q)];
 #pragma unroll
-        for (int q = 1; q < 8; ++q) v[q] = c_mul(v[q], g_twiddle[k * q * (kTwN / 512)]);
+        for (int q = 1; q < 8; ++q) v[q] = c_mul(v[q], g_tw8_s3b[(q - 1) * 64 + k]);
         dft8(v);
         if constexpr (N == 512) {
 #pragma unroll
@@ -357,7 +387,7 @@ fused_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
 #pragma unroll
             for (int q = 0; q < R; ++q) u[q] = buf_a[swz(jj + 512 * q)];
 #pragma unroll
-            for (int q = 1; q < R; ++q) u[q] = c_mul(u[q], g_twiddle[jj * q * (kTwN / N)]);
+            for (int q = 1; q < R; ++q) u[q] = c_mul(u[q], g_tw8_s4[tw8_s4_offset(N) + (q - 1) * 512 + jj]);
             if constexpr (R == 2) {
               bfly2(u[0], u[1]);
             } else if constexpr (R == 4) {
