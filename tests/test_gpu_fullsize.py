@@ -1,0 +1,145 @@
+"""GPU: BASELINE.json's full sizes through size-independent properties (the oracle would need
+minutes-hours there), plus spot checks of the same launch against the oracle.
+
+Properties used (all follow from features.py:17-185):
+  * scaling   x -> c*x (c > 0):  f6 *= c, f7 *= sqrt(c), f1 and f10,f11 *= c^2, f12-14 *= c^4,
+                                 f15-18 *= c^6, phase/frequency/kurtosis features unchanged;
+  * conjugation x -> conj(x):    every feature unchanged (|.|, std and kurtosis are even, |C_pq| too);
+  * batch independence:          a frame's row does not depend on its position / neighbours;
+  * agreement of the fused kernel with the general (FP64) kernel on the same device buffer.
+"""
+
+import numpy as np
+import pytest
+
+from conftest import assert_features_close
+
+pytestmark = pytest.mark.gpu
+
+POW = {1: 2, 6: 1, 7: 0.5, 10: 2, 11: 2, 12: 4, 13: 4, 14: 4, 15: 6, 16: 6, 17: 6, 18: 6}   # others: 0
+
+
+@pytest.fixture(scope="module")
+def config2_batch():
+    """BASELINE config 2: 6 modulations x 16 SNRs x 500 frames x 2048 samples, complex128, on the device."""
+    import torch
+
+    from amcpy_b200 import _native as nat
+    from amcpy_b200 import ops, synth
+
+    nat.require_cuda()
+    x = synth.dataset_torch(6, 16, 500, 2048, torch.device("cuda"), seed=77)
+    return torch, ops, x, ops.extract_features(x)
+
+
+def test_config2_shapes_finiteness_and_ranges(config2_batch):
+    torch, ops, x, f = config2_batch
+    assert tuple(f.shape) == (48000, 18) and f.dtype == torch.float64
+    assert bool(torch.isfinite(f).all())
+    fm = f.view(6, 16, 500, 18)
+    # sanity of the physics: mean |x| of unit-power constellations at 20 dB is ~1, WGN at 20 dB ~0.089
+    assert abs(float(fm[1, 15, :, 5].mean()) - 1.0) < 0.02
+    assert abs(float(fm[5, 15, :, 5].mean()) - 0.0886) < 0.005
+    # |C20| of BPSK ~ 1, of QPSK ~ 0 at high SNR; |C40| of QPSK ~ 1
+    assert float(fm[0, 15, :, 9].mean()) > 0.95 and float(fm[1, 15, :, 9].mean()) < 0.1
+    assert abs(float(fm[1, 15, :, 11].mean()) - 1.0) < 0.1
+
+
+def test_config2_spot_check_against_oracle(config2_batch):
+    from oracle import amc_oracle as orc
+
+    torch, ops, x, f = config2_batch
+    idx = torch.arange(0, 48000, 997, device=x.device)       # 49 frames spread over all (mod, snr) cells
+    want = orc.features_batch(x[idx].cpu().numpy())
+    assert_features_close(f[idx].cpu().numpy(), want)
+
+
+def test_config2_scaling_law(config2_batch):
+    torch, ops, x, f = config2_batch
+    c = 3.0
+    g = ops.extract_features(x * c)
+    for fid in range(1, 19):
+        p = POW.get(fid, 0)
+        rtol = 2e-6 if fid in (1, 2, 3, 5, 9) else 2e-9
+        a, b = g[:, fid - 1], f[:, fid - 1] * (c**p)
+        rel = ((a - b).abs() / b.abs().clamp_min(1e-300)).max().item()
+        assert rel <= rtol, f"feature {fid}: scaling law violated, rel {rel:.3e}"
+
+
+def test_config2_conjugation_invariance(config2_batch):
+    torch, ops, x, f = config2_batch
+    g = ops.extract_features(torch.conj(x).resolve_conj())
+    for fid in range(1, 19):
+        rtol = 2e-6 if fid in (1, 2, 3, 5, 9) else 2e-9
+        rel = ((g[:, fid - 1] - f[:, fid - 1]).abs() / f[:, fid - 1].abs().clamp_min(1e-300)).max().item()
+        assert rel <= rtol, f"feature {fid}: conj(x) changed the feature, rel {rel:.3e}"
+
+
+def test_config2_batch_order_and_grid_independence(config2_batch):
+    torch, ops, x, f = config2_batch
+    perm = torch.randperm(48000, device=x.device, generator=torch.Generator(device=x.device).manual_seed(3))
+    g = ops.extract_features(x[perm])
+    assert torch.equal(g, f[perm])                           # bitwise: fixed reduction order per frame
+    assert torch.equal(ops.extract_features(x[1000:1007]), f[1000:1007])
+
+
+def test_config2_fused_vs_general_kernel_all_frames_subset(config2_batch):
+    torch, ops, x, f = config2_batch
+    sub = x[::25]                                            # 1920 frames through the FP64 general kernel
+    g = ops.extract_features(sub, force_general=True)
+    assert_features_close(f[::25].cpu().numpy(), g.cpu().numpy(), scale=1.5)
+
+
+def test_many_frames_int64_indexing():
+    """300k frames x 512 samples (2.4 GB): frame offsets beyond 2^31 bytes, several waves per CTA."""
+    import torch
+
+    from amcpy_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((300_000, 512), dtype=torch.complex128, device="cuda", generator=g)
+    f = ops.extract_features(x)
+    assert bool(torch.isfinite(f).all())
+    tail = ops.extract_features(x[-64:].clone())
+    assert torch.equal(f[-64:], tail)
+    mid = ops.extract_features(x[150_000:150_032].clone())
+    assert torch.equal(f[150_000:150_032], mid)
+
+
+def test_noise_free_psk_goes_through_the_exact_tie_path():
+    """Noise-free BPSK/QPSK: most phase differences sit exactly on +-pi (np.unwrap's tie rule);
+    the fused kernel must agree with the reference semantics (FP64 general kernel / oracle)."""
+    import torch
+
+    from amcpy_b200 import ops
+    from oracle import amc_oracle as orc
+
+    rng = np.random.default_rng(11)
+    frames = []
+    for pts in (np.array([1, -1], dtype=complex), np.array([1, 1j, -1, -1j], dtype=complex),
+                np.array([1 + 1j, -1 + 1j, -1 - 1j, 1 - 1j], dtype=complex) * 3.0):
+        frames.append(pts[rng.integers(0, len(pts), 2048)])
+    x = np.stack(frames)
+    want = orc.features_batch(x)
+    got = ops.extract_features(torch.from_numpy(x).cuda()).cpu().numpy()
+    # frequency features (5, 9) depend on every tie decision; kurtosis of a constant amplitude (8) is 0/0
+    for fid in (2, 3, 5, 9, 6, 7, 10, 11, 12, 13, 14):
+        w, g_ = want[:, fid - 1], got[:, fid - 1]
+        assert np.allclose(g_, w, rtol=1e-6, atol=1e-9), (fid, g_, w)
+
+
+def test_low_snr_frames_tie_redecision_statistics():
+    """2,400 WGN / -10 dB frames (4.9 M phase differences): about 6 of them fall within 4e-6 rad of
+    +-pi, where a float32 atan2 cannot decide np.unwrap's branch.  The fused kernel re-decides those
+    in float64, so EVERY frame must stay inside the 1e-6 class (a single flipped branch moves
+    features 5 and 9 by ~1e-3)."""
+    import torch
+
+    from amcpy_b200 import ops, synth
+    from oracle import amc_oracle as orc
+
+    x = np.concatenate([synth.cell(5, 0.0, 5, range(1200), 2048, seed=31),
+                        synth.cell(1, -10.0, 0, range(1200), 2048, seed=32)])
+    want = orc.features_batch(x)
+    got = ops.extract_features(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert_features_close(got, want)
