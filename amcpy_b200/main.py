@@ -3,9 +3,9 @@
 Mirrors the reference's console script for the sub-commands that reach the hot path
 (/root/reference/src/amcpy/main.py:31-32 `extract`, :62-63 `full`, dispatch :160-175).  Unlike the
 reference - whose dispatcher passes (cfg, args) to the one-argument `cmd_extract` and raises
-TypeError (main.py:85 vs :175) - `extract` works.  `full` runs the extraction and then the feature
-consumer (column select + standardise + stratified split) so the matrices are proven loadable;
-plotting / classifier training are outside the hot path.
+TypeError (main.py:85 vs :175) - `extract` works.  `full` runs the extraction, the feature
+consumer (column select + standardise + stratified split) and the stock-PyTorch classifier
+(train + per-SNR accuracy); plotting is outside the path.
 `synth` writes a synthetic mat-data/all_modulations.mat the reference can consume as well.
 """
 
@@ -25,7 +25,8 @@ def _build_parser() -> argparse.ArgumentParser:
     p.add_argument("--frame-size", type=int, default=None, help="samples per frame (default 2048)")
     sub = p.add_subparsers(dest="command", required=True)
     sub.add_parser("extract", help="Extract features from raw .mat data")
-    sub.add_parser("full", help="extract, then load/standardise/split the feature matrices")
+    fp = sub.add_parser("full", help="extract -> standardise/split -> train/evaluate the classifier")
+    fp.add_argument("--epochs", type=int, default=None)
     s = sub.add_parser("synth", help="write a synthetic mat-data/all_modulations.mat")
     s.add_argument("--seed", type=int, default=2024)
     return p
@@ -56,12 +57,18 @@ def cmd_synth(cfg: Config, args) -> None:
 
 
 def cmd_full(cfg: Config, args=None) -> None:
+    from .classifier import accuracy_by_snr, train_classifier
     from .consumer import load_feature_set
 
     cmd_extract(cfg)
-    x_train, x_test, y_train, y_test, _ = load_feature_set(cfg, mode="training")
+    x_train, x_test, y_train, y_test, scaler = load_feature_set(cfg, mode="training")
     print(f"feature set ready: train {tuple(x_train.shape)}, test {tuple(x_test.shape)}, "
           f"{len(set(y_train.tolist()))} classes")
+    model, model_id, hist = train_classifier(cfg, x_train, y_train, x_test, y_test,
+                                             epochs=getattr(args, "epochs", None))
+    acc = accuracy_by_snr(model, scaler, cfg)
+    print(f"model {model_id}: val_acc {hist['val_accuracy'][-1]:.4f}; accuracy by SNR index: "
+          + ", ".join(f"{k}:{v:.2f}" for k, v in acc.items()))
 
 
 def main(argv=None) -> None:

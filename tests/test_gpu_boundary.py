@@ -229,3 +229,20 @@ def test_c_abi_error_codes(torch_cuda):
     with pytest.raises(nat.AmcError):
         nat.check(call(dt=7))
     torch_cuda.cuda.synchronize()
+
+
+# ------------------------------------------------------------------ BASELINE config 5: `amcpy full`
+def test_full_pipeline_extract_consume_train_eval(torch_cuda, tmp_path, capsys):
+    """synth -> extract (GPU) -> column select / standardise / split -> classifier train + per-SNR eval,
+    through the CLI entry (the reference's `amcpy full` cannot run: SURVEY.md App. B.1-B.3)."""
+    from amcpy_b200 import main as cli
+
+    root = str(tmp_path)
+    cli.main(["--root", root, "--num-frames", "60", "--frame-size", "1024", "synth", "--seed", "5"])
+    cli.main(["--root", root, "--num-frames", "60", "--frame-size", "1024", "full", "--epochs", "8"])
+    out = capsys.readouterr().out
+    assert "All feature calculations complete!" in out and "accuracy by SNR index" in out
+    assert len(list((tmp_path / "calculated-features").glob("*_features.mat"))) == 6
+    assert len(list((tmp_path / "ann").glob("model-*.pt"))) == 1
+    val_acc = float(out.split("val_acc ")[-1].split(";")[0])
+    assert val_acc > 0.6, out[-400:]            # 6 classes, chance = 0.17; high-SNR features separate them
