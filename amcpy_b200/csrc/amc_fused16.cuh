@@ -12,7 +12,10 @@
 //   * the edge phase (first sample after each warp's run of 32) travels through 64 bytes of shared
 //     memory instead of one shuffle per sample;
 //   * the 18-feature finalisation is batched: warp 0 parks each frame's 25 totals in shared memory
-//     and finalises 16 frames at once, one lane per frame, instead of 32 redundant lanes per frame.
+//     and finalises 16 frames at once, one lane per frame, instead of 32 redundant lanes per frame;
+//   * only TWO block barriers per frame: the FFT has its own two 16 KB buffers, so stage 1 (from
+//     registers) is written before the pass-1 barrier, the x slot is refilled by TMA right after
+//     that barrier, and a frame's totals are collected one frame later (double-buffered partials).
 #pragma once
 #include "amc_fused.cuh"
 
@@ -89,15 +92,13 @@ struct Fused16Cfg {
   static constexpr int CTA = GROUP < 128 ? 128 : GROUP;
   static constexpr int G = CTA / GROUP;
   static constexpr int W = GROUP / 32;
-  static constexpr int STAGES = 2;
-  static constexpr int SLOT_BYTES = N * static_cast<int>(sizeof(CT));
-  static constexpr bool C128 = sizeof(CT) == 16;
-  static constexpr int FFTB_BYTES = C128 ? 0 : N * 8;
+  static constexpr int SLOT_BYTES = N * static_cast<int>(sizeof(CT));   // one x slot (TMA target)
+  static constexpr int FFT_BYTES = N * 8;                               // each of the two FFT buffers
   static constexpr int PART_D = 20, PART_F = 12;
   static constexpr int PART_BYTES = PART_D * 8 + PART_F * 4;            // 208 per (parity, warp)
   static constexpr int EDGE_BYTES = W * 16 * 4;
   static constexpr int PEND_BYTES = 2 * kBatch * kPendStride * 8;       // 8448
-  static constexpr int GROUP_BYTES = STAGES * SLOT_BYTES + FFTB_BYTES + 2 * W * PART_BYTES + EDGE_BYTES + PEND_BYTES + 64;
+  static constexpr int GROUP_BYTES = SLOT_BYTES + 2 * FFT_BYTES + 2 * W * PART_BYTES + EDGE_BYTES + PEND_BYTES + 64;
   static constexpr int SMEM_BYTES = G * GROUP_BYTES;
   static constexpr int MIN_BLOCKS = (SMEM_BYTES <= 75 * 1024) ? 3 : ((SMEM_BYTES <= 113 * 1024) ? 2 : 1);
   static constexpr int R3 = N / 256;                     // radix of the last FFT stage: 2, 4, 8, 16
@@ -120,54 +121,84 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
   const int lane = tid & 31;
 
   unsigned char* gbase = smem_raw + static_cast<size_t>(g) * Cfg::GROUP_BYTES;
-  unsigned char* slots = gbase;
-  float2* fft_b_extra = reinterpret_cast<float2*>(gbase + Cfg::STAGES * Cfg::SLOT_BYTES);
-  unsigned char* part_base = gbase + Cfg::STAGES * Cfg::SLOT_BYTES + Cfg::FFTB_BYTES;
+  const CT* xs = reinterpret_cast<const CT*>(gbase);
+  float2* buf_a = reinterpret_cast<float2*>(gbase + Cfg::SLOT_BYTES);
+  float2* buf_b = reinterpret_cast<float2*>(gbase + Cfg::SLOT_BYTES + Cfg::FFT_BYTES);
+  unsigned char* part_base = gbase + Cfg::SLOT_BYTES + 2 * Cfg::FFT_BYTES;
   float* edge_s = reinterpret_cast<float*>(part_base + 2 * W * Cfg::PART_BYTES) + wg * 16;
   double* pend = reinterpret_cast<double*>(part_base + 2 * W * Cfg::PART_BYTES + Cfg::EDGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(part_base + 2 * W * Cfg::PART_BYTES + Cfg::EDGE_BYTES + Cfg::PEND_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(part_base + 2 * W * Cfg::PART_BYTES + Cfg::EDGE_BYTES + Cfg::PEND_BYTES);
 
   const int64_t gg = static_cast<int64_t>(blockIdx.x) * Cfg::G + g;
   const int64_t tg = static_cast<int64_t>(gridDim.x) * Cfg::G;
   const uint64_t policy = l2_evict_first_policy();
+  // frames this group will process in total
+  const int my_frames = (gg < n_frames) ? static_cast<int>((n_frames - gg + tg - 1) / tg) : 0;
 
   if (t == 0) {
-#pragma unroll
-    for (int s = 0; s < Cfg::STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_init(bar, 1);
     fence_mbar_init();
   }
   __syncthreads();
-  if (t == 0) {
-#pragma unroll
-    for (int s = 0; s < Cfg::STAGES; ++s) {
-      const int64_t f = gg + s * tg;
-      if (f < n_frames) {
-        mbar_arrive_expect_tx(&bars[s], Cfg::SLOT_BYTES);
-        bulk_copy_g2s(slots + s * Cfg::SLOT_BYTES, iq + f * frame_stride, Cfg::SLOT_BYTES, &bars[s], policy);
-      }
-    }
+  if (t == 0 && my_frames > 0) {
+    mbar_arrive_expect_tx(bar, Cfg::SLOT_BYTES);
+    bulk_copy_g2s(gbase, iq + gg * frame_stride, Cfg::SLOT_BYTES, bar, policy);
   }
+
+  auto part_d = [&](int par, int w) { return reinterpret_cast<double*>(part_base + (par * W + w) * Cfg::PART_BYTES); };
+  auto part_f = [&](int par, int w) {
+    return reinterpret_cast<float*>(part_base + (par * W + w) * Cfg::PART_BYTES + Cfg::PART_D * 8);
+  };
+  // warp 0: collect frame k's totals (25 values, lane i owns value i) and finalise 16 frames at a time
+  auto park_and_finalize = [&](int k) {
+    const int par = k & 1, bi = k % kBatch, half = (k / kBatch) & 1;
+    double* pe = pend + (half * kBatch + bi) * kPendStride;
+    if (lane < 19) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) s += part_d(par, w)[lane];
+      pe[lane] = s;
+    } else if (lane < 25) {
+      // 19..22 <- float sums 4..7 ; 23 <- sum f (float 2) ; 24 <- spectral max (float 8)
+      const int src = (lane < 23) ? (lane - 15) : (lane == 23 ? 2 : 8);
+      float s = part_f(par, 0)[src];
+#pragma unroll
+      for (int w = 1; w < W; ++w) s = (lane == 24) ? fmaxf(s, part_f(par, w)[src]) : s + part_f(par, w)[src];
+      pe[lane] = static_cast<double>(s);
+    }
+    if (bi == kBatch - 1 || k == my_frames - 1) {
+      __syncwarp();
+      if (lane <= bi) {
+        const double* pl = pend + (half * kBatch + lane) * kPendStride;
+        FrameSums fs;
+#pragma unroll
+        for (int i = 0; i < 15; ++i) fs.mono[i] = pl[i];
+        fs.sum_r = pl[15];
+        fs.c_abs1 = pl[16];
+        fs.c2 = pl[17];
+        fs.c4 = pl[18];
+        fs.ph_m2 = pl[19];
+        fs.aph_m2 = pl[20];
+        fs.f_m2 = pl[21];
+        fs.f_m4 = pl[22];
+        fs.mean_f = pl[23] / (N - 1);
+        fs.spec_max = pl[24];
+        const int64_t fo = gg + static_cast<int64_t>(k - bi + lane) * tg;
+        finalize_features(fs, N, out + fo * out_stride);
+      }
+      __syncwarp();
+    }
+  };
 
   // loop-invariant exchange offsets (float2 units)
   const int tx = t & 15;
   const int u0 = t ^ ((t >> 4) & 15);                 // swizzled position of element t (+ multiples of GROUP)
   const int w2base = (t >> 4) * 256;                  // stage-2 output block of this thread
 
-  // frames this group will process in total (for the batched finalisation)
-  const int my_frames = (gg < n_frames) ? static_cast<int>((n_frames - gg + tg - 1) / tg) : 0;
-
   for (int it = 0; it < my_frames; ++it) {
-    const int64_t f = gg + static_cast<int64_t>(it) * tg;
-    const int slot = it & 1;
-    const uint32_t parity = (it >> 1) & 1;
-    unsigned char* slot_ptr = slots + slot * Cfg::SLOT_BYTES;
-    const CT* xs = reinterpret_cast<const CT*>(slot_ptr);
-    auto part_d = [&](int w) { return reinterpret_cast<double*>(part_base + (slot * W + w) * Cfg::PART_BYTES); };
-    auto part_f = [&](int w) {
-      return reinterpret_cast<float*>(part_base + (slot * W + w) * Cfg::PART_BYTES + Cfg::PART_D * 8);
-    };
+    const int par = it & 1;
 
-    mbar_wait(&bars[slot], parity);
+    mbar_wait(bar, static_cast<uint32_t>(par));        // frame `it` has landed in the x slot
 
     // ---------------------------------------------------------------- pass 1
     Monomials mono;
@@ -245,20 +276,44 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       warp_sum_multi<double, 16>(acc, lane);
       float accf[4] = {s_ph, s_aph, s_f, 0.0f};
       warp_sum_multi<float, 4>(accf, lane);
-      if ((lane & 1) == 0) part_d(wg)[lane >> 1] = acc[0];
-      if ((lane & 7) == 0) part_f(wg)[lane >> 3] = accf[0];
+      if ((lane & 1) == 0) part_d(par, wg)[lane >> 1] = acc[0];
+      if ((lane & 7) == 0) part_f(par, wg)[lane >> 3] = accf[0];
     }
 
-    group_sync<GROUP, Cfg::CTA>(g);   // (1) pass-1 partials visible; the slot has been fully read
+    // ---------------------------------------------------------------- FFT stage 1 (Ns = 1), from registers
+    float2 v[16];
+    float2 tw2[15];
+#ifndef AMC_EXP_NO_FFT
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = make_float2(xr[q], xi[q]);
+    dft16(v);
+    {
+      float2* row = buf_a + 16 * t;                       // element 16 t + q -> position q ^ (t & 15)
+#pragma unroll
+      for (int q = 0; q < 16; ++q) row[q ^ tx] = v[bitrev4(q)];
+    }
+    // twiddles of the next stage are fetched BEFORE the barrier so their latency hides behind it
+#pragma unroll
+    for (int q = 1; q < 16; ++q) tw2[q - 1] = g_tw_s2[(q - 1) * 16 + tx];   // one 128-byte line per load
+#endif
+
+    group_sync<GROUP, Cfg::CTA>(g);   // (1) pass-1 partials + FFT stage-1 output visible; x slot fully read
+
+    if (t == 0 && it + 1 < my_frames) {                 // refill the x slot: frame it+1 streams in during pass 2 + FFT
+      fence_proxy_async_smem();
+      mbar_arrive_expect_tx(bar, Cfg::SLOT_BYTES);
+      bulk_copy_g2s(gbase, iq + (gg + static_cast<int64_t>(it + 1) * tg) * frame_stride, Cfg::SLOT_BYTES, bar, policy);
+    }
+    if (wg == 0 && it > 0) park_and_finalize(it - 1);   // the previous frame's totals are complete now
 
     double tot_r = 0.0;
     float tot_ph = 0.0f, tot_aph = 0.0f, tot_f = 0.0f;
 #pragma unroll
     for (int w = 0; w < W; ++w) {
-      tot_r += part_d(w)[15];
-      tot_ph += part_f(w)[0];
-      tot_aph += part_f(w)[1];
-      tot_f += part_f(w)[2];
+      tot_r += part_d(par, w)[15];
+      tot_ph += part_f(par, w)[0];
+      tot_aph += part_f(par, w)[1];
+      tot_f += part_f(par, w)[2];
     }
     const double mu_r = tot_r * (1.0 / N);
     const float mu_ph = tot_ph * (1.0f / N), mu_aph = tot_aph * (1.0f / N);
@@ -288,153 +343,72 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       warp_sum_multi<double, 4>(c2acc, lane);
       warp_sum_multi<float, 4>(q2acc, lane);
       if ((lane & 7) == 0) {
-        part_d(wg)[16 + (lane >> 3)] = c2acc[0];
-        part_f(wg)[4 + (lane >> 3)] = q2acc[0];
+        part_d(par, wg)[16 + (lane >> 3)] = c2acc[0];
+        part_f(par, wg)[4 + (lane >> 3)] = q2acc[0];
       }
     }
 
-    // ---------------------------------------------------------------- spectral max: 16 x 16 x R3 FFT
-    float2* buf_a = reinterpret_cast<float2*>(slot_ptr);
-    float2* buf_b = Cfg::C128 ? reinterpret_cast<float2*>(slot_ptr + N * 8) : fft_b_extra;
     float vmax = 0.0f;
 #ifdef AMC_EXP_NO_FFT
     vmax = xr[0] + xi[15];
+    group_sync<GROUP, Cfg::CTA>(g);
 #else
+    // ---------------------------------------------------------------- FFT stage 2 (Ns = 16)
+    // element t + GROUP q ; (e >> 4) & 15 = (t >> 4) + (GROUP/16) q  (no carry)
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = buf_a[(u0 ^ (((GROUP / 16) * q) & 15)) + GROUP * q];
+#pragma unroll
+    for (int q = 1; q < 16; ++q) v[q] = c_mul(v[q], tw2[q - 1]);
+    dft16(v);
     {
-      float2 v[16];
-      // stage 1 (Ns = 1): inputs are this thread's 16 samples t + (N/16) q
+      // element 256 (t>>4) + 16 q + tx  ->  (e >> 4) & 15 = q
+      float2* blk = buf_b + w2base;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) v[q] = make_float2(xr[q], xi[q]);
-      dft16(v);
-      {
-        float2* row = buf_a + 16 * t;                       // element 16 t + q -> position q ^ (t & 15)
+      for (int q = 0; q < 16; ++q) blk[16 * q + (tx ^ q)] = v[bitrev4(q)];
+    }
+    float2 tw3[(16 / R3) * (R3 - 1)];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) row[q ^ tx] = v[bitrev4(q)];
-      }
-      // twiddles of the next stage are fetched BEFORE the barrier so their latency hides behind it
-      float2 tw2[15];
-      {
+    for (int bb = 0; bb < 16 / R3; ++bb) {
+      const int jj = t + GROUP * bb;
 #pragma unroll
-        for (int q = 1; q < 16; ++q) tw2[q - 1] = g_tw_s2[(q - 1) * 16 + tx];   // one 128-byte line per load
-      }
-#ifndef AMC_EXP_NO_BAR23
-      group_sync<GROUP, Cfg::CTA>(g);   // (2)
-#endif
+      for (int q = 1; q < R3; ++q) tw3[bb * (R3 - 1) + q - 1] = g_tw_s3[tw_s3_offset(N) + (q - 1) * 256 + jj];
+    }
 
-      // stage 2 (Ns = 16): element t + GROUP q ; (e >> 4) & 15 = (t >> 4) + (GROUP/16) q  (no carry)
-#pragma unroll
-      for (int q = 0; q < 16; ++q) v[q] = buf_a[(u0 ^ (((GROUP / 16) * q) & 15)) + GROUP * q];
-#pragma unroll
-#ifndef AMC_EXP_NO_TWMUL
-      for (int q = 1; q < 16; ++q) v[q] = c_mul(v[q], tw2[q - 1]);
-#else
-      v[1].x += tw2[0].x + tw2[14].y;
-#endif
-#ifndef AMC_EXP_NO_DFT2
-      dft16(v);
-#endif
-      {
-        // element 256 (t>>4) + 16 q + tx  ->  (e >> 4) & 15 = q
-        float2* blk = buf_b + w2base;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) blk[16 * q + (tx ^ q)] = v[bitrev4(q)];
-      }
-      float2 tw3[(16 / R3) * (R3 - 1)];
-#pragma unroll
-      for (int bb = 0; bb < 16 / R3; ++bb) {
-        const int jj = t + GROUP * bb;
-#pragma unroll
-        for (int q = 1; q < R3; ++q) tw3[bb * (R3 - 1) + q - 1] = g_tw_s3[tw_s3_offset(N) + (q - 1) * 256 + jj];
-      }
-#ifndef AMC_EXP_NO_BAR23
-      group_sync<GROUP, Cfg::CTA>(g);   // (3)
-#endif
+    group_sync<GROUP, Cfg::CTA>(g);   // (2) stage-2 output visible
 
-      // stage 3 (Ns = 256, last): radix R3, 256 butterflies per frame, 16/R3 per thread
+    // ---------------------------------------------------------------- FFT stage 3 (Ns = 256, last): radix R3
 #pragma unroll
-      for (int bb = 0; bb < 16 / R3; ++bb) {
-        const int jj = t + GROUP * bb;                      // 0..255
-        const int p0 = jj ^ ((jj >> 4) & 15);               // (e >> 4) & 15 = (jj >> 4) & 15 for e = jj + 256 q
-        float2 u[R3];
+    for (int bb = 0; bb < 16 / R3; ++bb) {
+      const int jj = t + GROUP * bb;                      // 0..255
+      const int p0 = jj ^ ((jj >> 4) & 15);               // (e >> 4) & 15 = (jj >> 4) & 15 for e = jj + 256 q
+      float2 u[R3];
 #pragma unroll
-        for (int q = 0; q < R3; ++q) u[q] = buf_b[p0 + 256 * q];
+      for (int q = 0; q < R3; ++q) u[q] = buf_b[p0 + 256 * q];
 #pragma unroll
-#ifndef AMC_EXP_NO_TWMUL
-        for (int q = 1; q < R3; ++q) u[q] = c_mul(u[q], tw3[bb * (R3 - 1) + q - 1]);
-#else
-        u[1].x += tw3[bb * (R3 - 1)].x + tw3[bb * (R3 - 1) + R3 - 2].y;
-#endif
-        if constexpr (R3 == 2) {
-          bfly2(u[0], u[1]);
-        } else if constexpr (R3 == 4) {
-          dft4(u[0], u[1], u[2], u[3]);
-        } else if constexpr (R3 == 8) {
-          float2(&u8)[8] = reinterpret_cast<float2(&)[8]>(u);
-          dft8(u8);
-        } else {
-          float2(&u16)[16] = reinterpret_cast<float2(&)[16]>(u);
-          dft16(u16);
-        }
-#pragma unroll
-        for (int q = 0; q < R3; ++q) vmax = fmaxf(vmax, fmaf(u[q].x, u[q].x, u[q].y * u[q].y));
+      for (int q = 1; q < R3; ++q) u[q] = c_mul(u[q], tw3[bb * (R3 - 1) + q - 1]);
+      if constexpr (R3 == 2) {
+        bfly2(u[0], u[1]);
+      } else if constexpr (R3 == 4) {
+        dft4(u[0], u[1], u[2], u[3]);
+      } else if constexpr (R3 == 8) {
+        float2(&u8)[8] = reinterpret_cast<float2(&)[8]>(u);
+        dft8(u8);
+      } else {
+        float2(&u16)[16] = reinterpret_cast<float2(&)[16]>(u);
+        dft16(u16);
       }
+#pragma unroll
+      for (int q = 0; q < R3; ++q) vmax = fmaxf(vmax, fmaf(u[q].x, u[q].x, u[q].y * u[q].y));
     }
 #endif
     vmax = warp_max(vmax);
-    if (lane == 0) part_f(wg)[8] = vmax;
+    if (lane == 0) part_f(par, wg)[8] = vmax;
+    // no barrier here: buf_b / the partial arrays of this parity are next written two barriers later
+  }
 
-    group_sync<GROUP, Cfg::CTA>(g);   // (4) all partials of this frame are in shared memory; slot free
-
-    if (t == 0) {
-      const int64_t fn = f + Cfg::STAGES * tg;
-      if (fn < n_frames) {
-        fence_proxy_async_smem();
-        mbar_arrive_expect_tx(&bars[slot], Cfg::SLOT_BYTES);
-        bulk_copy_g2s(slot_ptr, iq + fn * frame_stride, Cfg::SLOT_BYTES, &bars[slot], policy);
-      }
-    }
-    if (wg == 0) {
-      // park this frame's totals: lane i owns value i of the 25
-      const int bi = it % kBatch, half = (it / kBatch) & 1;
-      double* pe = pend + (half * kBatch + bi) * kPendStride;
-      if (lane < 19) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < W; ++w) s += part_d(w)[lane];
-        pe[lane] = s;
-      } else if (lane < 25) {
-        // 19..22 <- float sums 4..7 ; 23 <- sum f (float 2) ; 24 <- spectral max (float 8)
-        const int src = (lane < 23) ? (lane - 15) : (lane == 23 ? 2 : 8);
-        float s = part_f(0)[src];
-#pragma unroll
-        for (int w = 1; w < W; ++w) s = (lane == 24) ? fmaxf(s, part_f(w)[src]) : s + part_f(w)[src];
-        pe[lane] = static_cast<double>(s);
-      }
-      const bool last = (it == my_frames - 1);
-      if (bi == kBatch - 1 || last) {
-        __syncwarp();
-        const int cnt = bi + 1;
-        if (lane < cnt) {
-          const double* pl = pend + (half * kBatch + lane) * kPendStride;
-          FrameSums fs;
-#pragma unroll
-          for (int i = 0; i < 15; ++i) fs.mono[i] = pl[i];
-          fs.sum_r = pl[15];
-          fs.c_abs1 = pl[16];
-          fs.c2 = pl[17];
-          fs.c4 = pl[18];
-          fs.ph_m2 = pl[19];
-          fs.aph_m2 = pl[20];
-          fs.f_m2 = pl[21];
-          fs.f_m4 = pl[22];
-          fs.mean_f = pl[23] / (N - 1);
-          fs.spec_max = pl[24];
-          const int64_t fo = gg + static_cast<int64_t>(it - bi + lane) * tg;
-          finalize_features(fs, N, out + fo * out_stride);
-        }
-        __syncwarp();
-      }
-    }
+  if (my_frames > 0) {                                  // (uniform per group)
+    group_sync<GROUP, Cfg::CTA>(g);                     // the last frame's spectral max is visible
+    if (wg == 0) park_and_finalize(my_frames - 1);
   }
 }
 
