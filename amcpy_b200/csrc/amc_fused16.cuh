@@ -82,7 +82,11 @@ __global__ void init_twiddle16_kernel() {
 // conflict-free exchange layout for the 16 x 16 x R Stockham passes: low 4 bits ^= bits 4..7
 __device__ __forceinline__ int swz16(int e) { return e ^ ((e >> 4) & 15); }
 
+#ifdef AMC_F16_INPLACE
+constexpr int kBatch = 8;         // (A/B build: in-place FFT buffer, 4 CTAs/SM at 128 registers)
+#else
 constexpr int kBatch = 16;        // frames finalised together (one lane each)
+#endif
 constexpr int kPendStride = 33;   // doubles per parked frame (32 + 1 pad: conflict-free lane-per-frame reads)
 
 template <int N, typename CT>
@@ -98,9 +102,14 @@ struct Fused16Cfg {
   static constexpr int PART_BYTES = PART_D * 8 + PART_F * 4;            // 208 per (parity, warp)
   static constexpr int EDGE_BYTES = W * 16 * 4;
   static constexpr int PEND_BYTES = 2 * kBatch * kPendStride * 8;       // 8448
-  static constexpr int GROUP_BYTES = SLOT_BYTES + 2 * FFT_BYTES + 2 * W * PART_BYTES + EDGE_BYTES + PEND_BYTES + 64;
+#ifdef AMC_F16_INPLACE
+  static constexpr int N_FFT_BUF = 1;
+#else
+  static constexpr int N_FFT_BUF = 2;
+#endif
+  static constexpr int GROUP_BYTES = SLOT_BYTES + N_FFT_BUF * FFT_BYTES + 2 * W * PART_BYTES + EDGE_BYTES + PEND_BYTES + 64;
   static constexpr int SMEM_BYTES = G * GROUP_BYTES;
-  static constexpr int MIN_BLOCKS = (SMEM_BYTES <= 75 * 1024) ? 3 : ((SMEM_BYTES <= 113 * 1024) ? 2 : 1);
+  static constexpr int MIN_BLOCKS = (SMEM_BYTES <= 55 * 1024 && CTA <= 128) ? 4 : (SMEM_BYTES <= 75 * 1024) ? 3 : ((SMEM_BYTES <= 113 * 1024) ? 2 : 1);
   static constexpr int R3 = N / 256;                     // radix of the last FFT stage: 2, 4, 8, 16
   static_assert(N >= 512 && N <= 4096 && GROUP % 32 == 0, "frame size outside the 16-samples-per-thread kernel");
   static_assert(GROUP_BYTES % 16 == 0, "group region must keep 16-byte alignment");
@@ -123,8 +132,8 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
   unsigned char* gbase = smem_raw + static_cast<size_t>(g) * Cfg::GROUP_BYTES;
   const CT* xs = reinterpret_cast<const CT*>(gbase);
   float2* buf_a = reinterpret_cast<float2*>(gbase + Cfg::SLOT_BYTES);
-  float2* buf_b = reinterpret_cast<float2*>(gbase + Cfg::SLOT_BYTES + Cfg::FFT_BYTES);
-  unsigned char* part_base = gbase + Cfg::SLOT_BYTES + 2 * Cfg::FFT_BYTES;
+  float2* buf_b = reinterpret_cast<float2*>(gbase + Cfg::SLOT_BYTES + (Cfg::N_FFT_BUF - 1) * Cfg::FFT_BYTES);
+  unsigned char* part_base = gbase + Cfg::SLOT_BYTES + Cfg::N_FFT_BUF * Cfg::FFT_BYTES;
   float* edge_s = reinterpret_cast<float*>(part_base + 2 * W * Cfg::PART_BYTES) + wg * 16;
   double* pend = reinterpret_cast<double*>(part_base + 2 * W * Cfg::PART_BYTES + Cfg::EDGE_BYTES);
   uint64_t* bar = reinterpret_cast<uint64_t*>(part_base + 2 * W * Cfg::PART_BYTES + Cfg::EDGE_BYTES + Cfg::PEND_BYTES);
@@ -360,32 +369,27 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
 #pragma unroll
     for (int q = 1; q < 16; ++q) v[q] = c_mul(v[q], tw2[q - 1]);
     dft16(v);
+    if constexpr (Cfg::N_FFT_BUF == 1) group_sync<GROUP, Cfg::CTA>(g);   // in-place: every stage-2 read is done
     {
       // element 256 (t>>4) + 16 q + tx  ->  (e >> 4) & 15 = q
       float2* blk = buf_b + w2base;
 #pragma unroll
       for (int q = 0; q < 16; ++q) blk[16 * q + (tx ^ q)] = v[bitrev4(q)];
     }
-    float2 tw3[(16 / R3) * (R3 - 1)];
-#pragma unroll
-    for (int bb = 0; bb < 16 / R3; ++bb) {
-      const int jj = t + GROUP * bb;
-#pragma unroll
-      for (int q = 1; q < R3; ++q) tw3[bb * (R3 - 1) + q - 1] = g_tw_s3[tw_s3_offset(N) + (q - 1) * 256 + jj];
-    }
-
     group_sync<GROUP, Cfg::CTA>(g);   // (2) stage-2 output visible
 
     // ---------------------------------------------------------------- FFT stage 3 (Ns = 256, last): radix R3
-#pragma unroll
+#pragma unroll 1
     for (int bb = 0; bb < 16 / R3; ++bb) {
       const int jj = t + GROUP * bb;                      // 0..255
       const int p0 = jj ^ ((jj >> 4) & 15);               // (e >> 4) & 15 = (jj >> 4) & 15 for e = jj + 256 q
-      float2 u[R3];
+      float2 u[R3], w3[R3 - 1];
+#pragma unroll
+      for (int q = 1; q < R3; ++q) w3[q - 1] = g_tw_s3[tw_s3_offset(N) + (q - 1) * 256 + jj];
 #pragma unroll
       for (int q = 0; q < R3; ++q) u[q] = buf_b[p0 + 256 * q];
 #pragma unroll
-      for (int q = 1; q < R3; ++q) u[q] = c_mul(u[q], tw3[bb * (R3 - 1) + q - 1]);
+      for (int q = 1; q < R3; ++q) u[q] = c_mul(u[q], w3[q - 1]);
       if constexpr (R3 == 2) {
         bfly2(u[0], u[1]);
       } else if constexpr (R3 == 4) {
