@@ -88,6 +88,7 @@ SIGNATURES = {
     "amc_frames_from_sample_major": (_INT, [_P, _INT, _I64, _I64, _I64, _P, _P]),
     "amc_instantaneous_batch": (_INT, [_P, _INT, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "amc_moments_batch": (_INT, [_P, _INT, _I64, _I64, _I64, _I64, _P, _P]),
+    "amc_generate_frames": (_INT, [_P, _INT, _INT, _I64, _I64, _I64, _P, _P, _P, ctypes.c_uint64, _P]),
 }
 
 

@@ -10,6 +10,7 @@
 #include "amc_fused.cuh"
 #include "amc_fused16.cuh"
 #include "amc_general.cuh"
+#include "amc_generate.cuh"
 
 namespace {
 
@@ -350,6 +351,32 @@ int amc_moments_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t fr
   else
     amc::moments_kernel<float2><<<grid, amc::kGenThreads, 0, stream>>>(
         static_cast<const float2*>(iq), n_frames, static_cast<int>(frame_size), frame_stride, sample_stride, out);
+  ++t_launches;
+  AMC_CUDA(cudaGetLastError());
+  return AMC_OK;
+}
+
+int amc_generate_frames(void* out, int iq_dtype, int n_cells, int64_t frames_per_cell, int64_t first_frame,
+                        int64_t frame_size, const int* cell_mod, const int* cell_snr_idx, const double* cell_sigma,
+                        uint64_t seed, void* cuda_stream) {
+  if (iq_dtype != AMC_C64 && iq_dtype != AMC_C128) return fail(AMC_ERR_INVALID_ARG, "iq_dtype %d unknown", iq_dtype);
+  if (n_cells < 0 || frames_per_cell < 0 || frame_size < 1 || frame_size > (1 << 30) || first_frame < 0)
+    return fail(AMC_ERR_INVALID_ARG, "bad generator shape");
+  if (n_cells == 0 || frames_per_cell == 0) return AMC_OK;
+  if (!out || !cell_mod || !cell_snr_idx || !cell_sigma) return fail(AMC_ERR_INVALID_ARG, "NULL pointer");
+  DevInfo di;
+  int rc = device_info(&di);
+  if (rc != AMC_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const int grid = di.sms * 8;
+  if (iq_dtype == AMC_C128)
+    amc::generate_frames_kernel<double2><<<grid, 256, 0, stream>>>(static_cast<double2*>(out), n_cells, frames_per_cell,
+                                                                   first_frame, static_cast<int>(frame_size), cell_mod,
+                                                                   cell_snr_idx, cell_sigma, seed);
+  else
+    amc::generate_frames_kernel<float2><<<grid, 256, 0, stream>>>(static_cast<float2*>(out), n_cells, frames_per_cell,
+                                                                  first_frame, static_cast<int>(frame_size), cell_mod,
+                                                                  cell_snr_idx, cell_sigma, seed);
   ++t_launches;
   AMC_CUDA(cudaGetLastError());
   return AMC_OK;

@@ -105,3 +105,29 @@ def dataset_torch(n_mods: int, n_snr: int, n_frames: int, n: int, device, seed: 
             out[mi, si] = z
             del re, im, z
     return out.reshape(n_mods * n_snr * n_frames, n)
+
+
+def dataset_device(n_mods: int, snr_dbs, n_frames: int, n: int, device, seed: int = 2024, first_frame: int = 0,
+                   dtype=None, mods=None):
+    """Hand-written CUDA generator (C ABI `amc_generate_frames`): (n_mods*n_snr*n_frames, n) complex on
+    `device`, cells ordered (modulation, snr).  Counter-based: `first_frame` selects a shard of the
+    frame axis that is bit-identical to the same frames of the full set."""
+    import torch
+
+    from . import _native as nat
+
+    dtype = dtype or torch.complex128
+    snr_dbs = list(snr_dbs)
+    mods = list(mods) if mods is not None else list(range(n_mods))
+    cell_mod = torch.tensor([m % 6 for m in mods for _ in snr_dbs], dtype=torch.int32, device=device)
+    cell_snr = torch.tensor([si for _ in mods for si in range(len(snr_dbs))], dtype=torch.int32, device=device)
+    cell_sig = torch.tensor([float(np.sqrt(10.0 ** (-s / 10.0) / 2.0)) for _ in mods for s in snr_dbs],
+                            dtype=torch.float64, device=device)
+    n_cells = cell_mod.numel()
+    out = torch.empty((n_cells * n_frames, n), dtype=dtype, device=device)
+    with torch.cuda.device(device):
+        rc = nat.lib().amc_generate_frames(
+            out.data_ptr(), nat.AMC_C128 if dtype == torch.complex128 else nat.AMC_C64, n_cells, n_frames, first_frame,
+            n, cell_mod.data_ptr(), cell_snr.data_ptr(), cell_sig.data_ptr(), seed, torch.cuda.current_stream().cuda_stream)
+    nat.check(rc)
+    return out

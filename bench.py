@@ -230,7 +230,8 @@ def run_cuda_arm(args):
 
     n_frames = N_MODS * N_SNR * N_FRAMES
     # rank-specific seed: every rank owns its own 48,000-frame batch (weak scaling)
-    x = synth.dataset_torch(N_MODS, N_SNR, N_FRAMES, FRAME, dev, seed=2024 + rank)
+    # hand-written on-device generator (counter-based Philox): rank r owns frames [r*500, (r+1)*500) of every cell
+    x = synth.dataset_device(N_MODS, SNRS, N_FRAMES, FRAME, dev, seed=2024, first_frame=rank * N_FRAMES)
     out = torch.empty((n_frames, 18), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
     lib = nat.lib()
@@ -244,7 +245,7 @@ def run_cuda_arm(args):
     # ---- device-resident timing: K launches, one CUDA-event pair per launch on the launching stream
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = lib.amc_launch_count()
+    launches0 = lib.amc_launch_count()   # counted from here: the generator / warm-up launches are excluded
     with ClockSampler(local_rank) as clocks:
         barrier()
         t_all0.record(stream)

@@ -123,6 +123,20 @@ int amc_instantaneous_batch(const void* iq, int iq_dtype, int64_t n_frames, int6
 int amc_moments_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size,
                       int64_t frame_stride, int64_t sample_stride, double* out, void* cuda_stream);
 
+/*
+ * On-device synthetic IQ frames (no reference counterpart: the reference's data came from captures,
+ * old/read_binary_stream.py:19-59; recipe of SURVEY.md section 8d).  Cell = one (modulation, SNR) pair:
+ *   cell_mod[c]      0 BPSK, 1 QPSK, 2 8PSK, 3 16QAM, 4 64QAM, 5 WGN      (device int array, n_cells)
+ *   cell_snr_idx[c]  SNR index used in the random-stream key               (device int array)
+ *   cell_sigma[c]    noise standard deviation per rail                     (device double array)
+ * out (device) receives [n_cells][frames_per_cell][frame_size] complex samples; frame numbering starts at
+ * first_frame, so any shard of the frame axis regenerates exactly the frames of the full set
+ * (Philox4x32-10 keyed by seed, counter = (sample, frame, snr index, modulation)).
+ */
+int amc_generate_frames(void* out, int iq_dtype, int n_cells, int64_t frames_per_cell, int64_t first_frame,
+                        int64_t frame_size, const int* cell_mod, const int* cell_snr_idx, const double* cell_sigma,
+                        uint64_t seed, void* cuda_stream);
+
 /* How many kernels of this library the calling thread has launched so far (for bench accounting). */
 int64_t amc_launch_count(void);
 

@@ -246,3 +246,32 @@ def test_full_pipeline_extract_consume_train_eval(torch_cuda, tmp_path, capsys):
     assert len(list((tmp_path / "ann").glob("model-*.pt"))) == 1
     val_acc = float(out.split("val_acc ")[-1].split(";")[0])
     assert val_acc > 0.6, out[-400:]            # 6 classes, chance = 0.17; high-SNR features separate them
+
+
+# ------------------------------------------------------------------ on-device generator
+def test_device_generator_recipe_determinism_and_shards(torch_cuda):
+    from amcpy_b200 import ops, synth
+    from oracle import amc_oracle as orc
+
+    snrs = [-10.0, 0.0, 20.0]
+    full = synth.dataset_device(6, snrs, 8, 2048, torch_cuda.device("cuda"), seed=99).view(6, 3, 8, 2048)
+    again = synth.dataset_device(6, snrs, 8, 2048, torch_cuda.device("cuda"), seed=99).view(6, 3, 8, 2048)
+    assert torch_cuda.equal(full, again)
+    shard = synth.dataset_device(6, snrs, 3, 2048, torch_cuda.device("cuda"), seed=99, first_frame=5).view(6, 3, 3, 2048)
+    assert torch_cuda.equal(shard, full[:, :, 5:8])                      # any frame shard == the same frames of the full set
+    other = synth.dataset_device(6, snrs, 8, 2048, torch_cuda.device("cuda"), seed=100).view(6, 3, 8, 2048)
+    assert not torch_cuda.equal(other, full)
+    p = (full.abs() ** 2).mean(dim=(2, 3)).cpu().numpy()                 # mean power per (mod, snr)
+    for m in range(5):
+        assert np.allclose(p[m], 1.0 + 10.0 ** (-np.array(snrs) / 10.0), rtol=0.05), (m, p[m])
+    assert np.allclose(p[5], 10.0 ** (-np.array(snrs) / 10.0), rtol=0.05)
+    x = full.cpu().numpy()
+    for m, name in enumerate(synth.MODULATIONS[:5]):                     # at 20 dB every sample sits near a constellation point
+        pts = synth.constellation(name)
+        d = np.abs(x[m, 2].reshape(-1)[:, None] - pts[None, :]).min(axis=1)
+        assert np.percentile(d, 99) < 0.35, name
+        counts = np.bincount(np.abs(x[m, 2].reshape(-1)[:, None] - pts[None, :]).argmin(axis=1), minlength=len(pts))
+        assert counts.min() > 0.6 * counts.mean(), (name, counts)        # symbols roughly uniform
+    # features of generated frames agree with the oracle on the same bits
+    sub = full[:, 1, 0]                                                  # one 0 dB frame per class
+    assert_features_close(ops.extract_features(sub).cpu().numpy(), orc.features_batch(sub.cpu().numpy()))
