@@ -59,3 +59,49 @@ def load_feature_set(cfg: Config, mode: str = "training", matrices: dict | None 
     x_train, x_test, y_train, y_test = train_test_split(
         xs, y, test_size=cfg.training.test_size, random_state=cfg.training.random_state, stratify=y)
     return x_train, x_test, y_train, y_test, scaler
+
+
+# ------------------------------------------------------------------------------------------
+# device-resident form: fed straight from ops.extract_features, no .mat round trip
+# ------------------------------------------------------------------------------------------
+def stack_features_device(cfg: Config, feats: dict, mode: str = "training"):
+    """feats: {MOD: CUDA float64/float32 tensor (n_snr, n_frames, 18)} -> (x float32 (n, n_used), y int64),
+    same row order as `stack_features` (modulation, then SNR of the chosen axis, then frame)."""
+    import torch
+
+    s, t, f = cfg.signals, cfg.training, cfg.features
+    snr_axis = list(t.training_snr if mode == "training" else t.all_snr)
+    cols = list(f.used)
+    xs, ys = [], []
+    for mod_idx, mod in enumerate(s.modulations_with_noise):
+        m = feats[mod][snr_axis][:, : s.num_frames][:, :, cols]          # (n_sel_snr, n_frames, n_used)
+        xs.append(m.reshape(-1, len(cols)).to(torch.float32))            # float32 like the reference's .mat
+        ys.append(torch.full((m.shape[0] * m.shape[1],), s.labels[mod_idx], dtype=torch.int64, device=m.device))
+    return torch.cat(xs), torch.cat(ys)
+
+
+def standardize_device(x):
+    """(x - mean) / std with StandardScaler's conventions, on the device; returns (x_std, mean, scale)."""
+    import torch
+
+    x64 = x.to(torch.float64)
+    mean = x64.mean(dim=0)
+    var = x64.var(dim=0, unbiased=False)
+    scale = torch.where(var > 0, var.sqrt(), torch.ones_like(var))
+    return ((x64 - mean) / scale).to(torch.float32), mean, scale
+
+
+def stratified_split_device(x, y, test_size: float, seed: int):
+    """Per-class random split (same class proportions in both parts), all on the device."""
+    import torch
+
+    g = torch.Generator(device=x.device).manual_seed(seed)
+    tr, te = [], []
+    for c in torch.unique(y).tolist():
+        idx = torch.nonzero(y == c, as_tuple=False).flatten()
+        idx = idx[torch.randperm(idx.numel(), device=x.device, generator=g)]
+        k = int(round(idx.numel() * test_size))
+        te.append(idx[:k])
+        tr.append(idx[k:])
+    tr, te = torch.cat(tr), torch.cat(te)
+    return x[tr], x[te], y[tr], y[te]

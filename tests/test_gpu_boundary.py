@@ -275,3 +275,24 @@ def test_device_generator_recipe_determinism_and_shards(torch_cuda):
     # features of generated frames agree with the oracle on the same bits
     sub = full[:, 1, 0]                                                  # one 0 dB frame per class
     assert_features_close(ops.extract_features(sub).cpu().numpy(), orc.features_batch(sub.cpu().numpy()))
+
+
+def test_device_consumer_matches_host_consumer(torch_cuda):
+    from amcpy_b200 import ops, synth
+    from amcpy_b200.config import Config, SignalConfig
+    from amcpy_b200.consumer import (Standardizer, stack_features, stack_features_device, standardize_device,
+                                     stratified_split_device)
+
+    cfg = Config(signals=SignalConfig(num_frames=12, frame_size=512))
+    snrs = [float(v) for v in cfg.signals.snr_values.values()]
+    x = synth.dataset_device(6, snrs, 12, 512, torch_cuda.device("cuda"), seed=4).view(6, 16, 12, 512)
+    feats = {m: ops.extract_features(x[i]) for i, m in enumerate(cfg.signals.modulations_with_noise)}
+    xd, yd = stack_features_device(cfg, feats, "training")
+    xh, yh = stack_features(cfg, "training", {m: v.cpu().numpy().astype(np.float32) for m, v in feats.items()})
+    assert np.array_equal(xd.cpu().numpy(), xh) and np.array_equal(yd.cpu().numpy(), yh)
+    xs, mean, scale = standardize_device(xd)
+    sc = Standardizer().fit(xh)
+    assert np.allclose(xs.cpu().numpy(), sc.transform(xh), rtol=1e-5, atol=1e-6)
+    xtr, xte, ytr, yte = stratified_split_device(xs, yd, cfg.training.test_size, cfg.training.random_state)
+    assert xtr.shape[0] + xte.shape[0] == xs.shape[0] and xte.shape[0] == round(0.2 * xs.shape[0])
+    assert torch_cuda.bincount(yte).tolist() == [round(0.2 * 72)] * 6
