@@ -294,5 +294,5 @@ def test_device_consumer_matches_host_consumer(torch_cuda):
     sc = Standardizer().fit(xh)
     assert np.allclose(xs.cpu().numpy(), sc.transform(xh), rtol=1e-5, atol=1e-6)
     xtr, xte, ytr, yte = stratified_split_device(xs, yd, cfg.training.test_size, cfg.training.random_state)
-    assert xtr.shape[0] + xte.shape[0] == xs.shape[0] and xte.shape[0] == round(0.2 * xs.shape[0])
+    assert xtr.shape[0] + xte.shape[0] == xs.shape[0] and xte.shape[0] == 6 * round(0.2 * 72)
     assert torch_cuda.bincount(yte).tolist() == [round(0.2 * 72)] * 6
