@@ -9,6 +9,7 @@
 
 #include "amc_fused.cuh"
 #include "amc_fused16.cuh"
+#include "amc_fusedw.cuh"
 #include "amc_general.cuh"
 #include "amc_generate.cuh"
 
@@ -124,11 +125,37 @@ int launch_fused16(const void* iq, int64_t n_frames, int64_t frame_stride, doubl
   return AMC_OK;
 }
 
+template <int N, typename CT>
+int launch_fusedw(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride,
+                  int sms, cudaStream_t stream) {
+  using Cfg = amc::FusedWCfg<N, CT>;
+  auto kern = amc::fusedw_features_kernel<N, CT>;
+  static thread_local int blocks_per_sm[kMaxDevices] = {};
+  int dev = 0;
+  AMC_CUDA(cudaGetDevice(&dev));
+  if (blocks_per_sm[dev] == 0) {
+    AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int occ = 0;
+    AMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::CTA, Cfg::SMEM_BYTES));
+    if (occ < 1) return fail(AMC_ERR_CUDA, "warp-per-frame kernel N=%d does not fit on this device", N);
+    blocks_per_sm[dev] = occ;
+  }
+  const int64_t want = (n_frames + Cfg::G - 1) / Cfg::G;
+  const int64_t cap = static_cast<int64_t>(sms) * blocks_per_sm[dev];
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  kern<<<grid, Cfg::CTA, Cfg::SMEM_BYTES, stream>>>(static_cast<const CT*>(iq), n_frames, frame_stride, out,
+                                                   out_stride);
+  ++t_launches;
+  AMC_CUDA(cudaGetLastError());
+  return AMC_OK;
+}
+
 template <typename CT>
 int dispatch_fused(int64_t n, const void* iq, int64_t n_frames, int64_t frame_stride, double* out,
                    int64_t out_stride, int sms, cudaStream_t stream, bool spt8) {
   if (!spt8) {
     switch (n) {
+      case 256: return launch_fusedw<256, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
       case 512: return launch_fused16<512, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
       case 1024: return launch_fused16<1024, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
       case 2048: return launch_fused16<2048, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
