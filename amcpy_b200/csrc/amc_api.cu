@@ -10,6 +10,7 @@
 #include "amc_fused.cuh"
 #include "amc_fused16.cuh"
 #include "amc_fusedw.cuh"
+#include "amc_large.cuh"
 #include "amc_general.cuh"
 #include "amc_generate.cuh"
 
@@ -66,7 +67,8 @@ int ensure_twiddles(int dev, cudaStream_t stream) {
   amc::init_twiddle_kernel<<<amc::kTwN / 256, 256, 0, stream>>>();
   amc::init_twiddle16_kernel<<<26, 256, 0, stream>>>();
   amc::init_twiddle8_kernel<<<22, 256, 0, stream>>>();
-  t_launches += 3;
+  amc::init_twiddle_large_kernel<<<64, 256, 0, stream>>>();
+  t_launches += 4;
   AMC_CUDA(cudaGetLastError());
   AMC_CUDA(cudaStreamSynchronize(stream));  // once per device: later calls on other streams may rely on it
   g_tw_ready[dev] = true;
@@ -150,6 +152,20 @@ int launch_fusedw(const void* iq, int64_t n_frames, int64_t frame_stride, double
   return AMC_OK;
 }
 
+template <int N, typename CT>
+int launch_large(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride, int sms,
+                 cudaStream_t stream) {
+  using Cfg = amc::LargeCfg<N>;
+  auto kern = amc::large_features_kernel<N, CT>;
+  AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int grid = static_cast<int>(n_frames < sms ? n_frames : sms);
+  kern<<<grid, amc::kLargeThreads, Cfg::SMEM_BYTES, stream>>>(static_cast<const CT*>(iq), n_frames, frame_stride, out,
+                                                             out_stride);
+  ++t_launches;
+  AMC_CUDA(cudaGetLastError());
+  return AMC_OK;
+}
+
 template <typename CT>
 int dispatch_fused(int64_t n, const void* iq, int64_t n_frames, int64_t frame_stride, double* out,
                    int64_t out_stride, int sms, cudaStream_t stream, bool spt8) {
@@ -160,6 +176,8 @@ int dispatch_fused(int64_t n, const void* iq, int64_t n_frames, int64_t frame_st
       case 1024: return launch_fused16<1024, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
       case 2048: return launch_fused16<2048, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
       case 4096: return launch_fused16<4096, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 8192: return launch_large<8192, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 16384: return launch_large<16384, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
       default: break;
     }
   }
@@ -173,7 +191,9 @@ int dispatch_fused(int64_t n, const void* iq, int64_t n_frames, int64_t frame_st
   }
 }
 
-bool fused_size(int64_t n) { return n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096; }
+bool fused_size(int64_t n) {
+  return n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096 || n == 8192 || n == 16384;
+}
 
 constexpr int64_t kGeneralPow2Max = 16384;   // N float2 of FFT scratch must fit in shared memory
 constexpr int64_t kGeneralDftMax = 12288;    // N double2 of twiddles must fit in shared memory

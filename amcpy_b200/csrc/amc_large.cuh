@@ -1,0 +1,246 @@
+// Long frames (N = 8192, 16384): one 512-thread CTA per frame, persistent over frames.
+// The frame does not fit the "registers hold the whole frame" scheme of the fused kernels, so:
+//   pass 1 streams x from HBM (coalesced 16-byte loads): FP64 monomials + |x|, FP32 atan2; the
+//          FP32 copy of x goes to the FFT buffer and the phase to a phase buffer, both in shared memory;
+//   pass 1b forms the wrapped phase differences from the phase buffer (FP64 re-decision of ties);
+//   pass 2 re-reads x (L2-resident: 148 CTAs x 256 KB < L2) for the centred amplitude sums and the
+//          phase buffer for the centred phase / frequency sums;
+//   FFT    in-place Stockham, radix 16 x 16 x 16 x (N/4096), XOR-swizzled, lane-contiguous twiddle tables.
+// Same numerics / tolerances as the fused kernels.
+#pragma once
+#include "amc_fused16.cuh"
+
+namespace amc {
+
+constexpr int kLargeThreads = 512;
+constexpr int kLargeWarps = kLargeThreads / 32;
+
+// g_tw_l4[off(N) + q-1][j] = W_N^(j q), j < 4096, q = 1..N/4096-1
+__device__ float2 g_tw_l4[4 * 4096];
+__host__ __device__ constexpr int tw_l4_offset(int n) { return (n == 8192 ? 0 : 1) * 4096; }
+__global__ void init_twiddle_large_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 4 * 4096) {
+    const int row = i / 4096, j = i % 4096;
+    const int n = row < 1 ? 8192 : 16384;
+    const int q = row < 1 ? 1 : row;
+    g_tw_l4[i] = tw_exact(j * q, n);
+  }
+}
+
+template <int N>
+struct LargeCfg {
+  static_assert(N == 8192 || N == 16384, "long-frame kernel sizes");
+  static constexpr int FFT_BYTES = N * 8;
+  static constexpr int PHI_BYTES = N * 4;
+  static constexpr int PART_BYTES = 2 * kLargeWarps * 32 * 8;      // two parities x 16 warps x 32 doubles
+  static constexpr int SMEM_BYTES = FFT_BYTES + PHI_BYTES + PART_BYTES + 64;
+  static constexpr int R4 = N / 4096;                              // radix of the last stage
+  static constexpr int BPT = (N / 16) / kLargeThreads;             // radix-16 butterflies per thread: 1 or 2
+};
+
+template <typename CT>
+__device__ __forceinline__ void load_global_sample(const CT* __restrict__ p, double& a, double& b, float& af, float& bf) {
+  load_sample<CT>(p, a, b, af, bf);
+}
+
+// one in-place radix-16 Stockham stage over the whole frame (BPT butterflies per thread)
+template <int N, int NS, int BPT>
+__device__ __forceinline__ void large_stage16(float2* __restrict__ buf, const float2* __restrict__ tw, int tid) {
+  float2 v[BPT][16];
+#pragma unroll
+  for (int bb = 0; bb < BPT; ++bb) {
+    const int j = tid + kLargeThreads * bb;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[bb][q] = buf[swz16(j + (N / 16) * q)];
+  }
+  __syncthreads();                                                 // all reads of this stage are done
+#pragma unroll
+  for (int bb = 0; bb < BPT; ++bb) {
+    const int j = tid + kLargeThreads * bb;
+    const int k = j % NS;
+    if constexpr (NS > 1) {
+#pragma unroll
+      for (int q = 1; q < 16; ++q) v[bb][q] = c_mul(v[bb][q], tw[(q - 1) * NS + k]);
+    }
+    dft16(v[bb]);
+    const int base = (j / NS) * NS * 16 + k;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) buf[swz16(base + NS * q)] = v[bb][bitrev4(q)];
+  }
+  __syncthreads();
+}
+
+template <int N, typename CT>
+__global__ void __launch_bounds__(kLargeThreads, 1)
+large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame_stride,
+                      double* __restrict__ out, int64_t out_stride) {
+  using Cfg = LargeCfg<N>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* buf = reinterpret_cast<float2*>(smem_raw);
+  float* phi = reinterpret_cast<float*>(smem_raw + Cfg::FFT_BYTES);
+  double* part = reinterpret_cast<double*>(smem_raw + Cfg::FFT_BYTES + Cfg::PHI_BYTES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr unsigned FULL = 0xffffffffu;
+
+  int it = 0;
+  for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x, ++it) {
+    const CT* x = iq + f * frame_stride;
+    double* pw = part + ((it & 1) * kLargeWarps + warp) * 32;       // this warp's 32 partial slots
+    double* pall = part + (it & 1) * kLargeWarps * 32;
+
+    // ---------------------------------------------------------------- pass 1
+    Monomials mono;
+    mono.clear();
+    double sum_r = 0.0;
+    float s_ph = 0.0f, s_aph = 0.0f;
+#pragma unroll 4
+    for (int i = tid; i < N; i += kLargeThreads) {
+      double a, b;
+      float af, bf;
+      load_global_sample<CT>(x + i, a, b, af, bf);
+      const double s = mono.add(a, b);
+      sum_r += sqrt_nr(s);
+      const float p = atan2_fast(bf, af);
+      buf[swz16(i)] = make_float2(af, bf);
+      phi[i] = p;
+      s_ph += p;
+      s_aph += fabsf(p);
+    }
+    __syncthreads();
+    // ---------------------------------------------------------------- pass 1b: sum of wrapped differences
+    float s_f = 0.0f;
+#pragma unroll 4
+    for (int i = tid; i < N - 1; i += kLargeThreads) {
+      float dd = phi[i + 1] - phi[i];
+      const float over = fabsf(dd) - kPiF;
+      float fj;
+      if (fabsf(over) < kTieEps) {
+        fj = exact_freq_step<CT>(x, i);
+      } else {
+        if (over > 0.0f) dd -= copysignf(kTwoPiF, dd);
+        fj = dd * kInvTwoPiF;
+      }
+      s_f += fj;
+    }
+    {
+      double acc[16];
+#pragma unroll
+      for (int i = 0; i < 15; ++i) acc[i] = mono.s[i];
+      acc[15] = sum_r;
+      warp_sum_multi<double, 16>(acc, lane);
+      float accf[4] = {s_ph, s_aph, s_f, 0.0f};
+      warp_sum_multi<float, 4>(accf, lane);
+      if ((lane & 1) == 0) pw[lane >> 1] = acc[0];                          // 0..15
+      if ((lane & 7) == 0) pw[16 + (lane >> 3)] = static_cast<double>(accf[0]);   // 16..19
+    }
+    __syncthreads();
+    double tot_r = 0.0, tot_ph = 0.0, tot_aph = 0.0, tot_f = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLargeWarps; ++w) {
+      tot_r += pall[w * 32 + 15];
+      tot_ph += pall[w * 32 + 16];
+      tot_aph += pall[w * 32 + 17];
+      tot_f += pall[w * 32 + 18];
+    }
+    const double mu_r = tot_r * (1.0 / N);
+    const float mu_ph = static_cast<float>(tot_ph * (1.0 / N)), mu_aph = static_cast<float>(tot_aph * (1.0 / N));
+    const float mu_f = static_cast<float>(tot_f * (1.0 / (N - 1)));
+
+    // ---------------------------------------------------------------- pass 2: centred sums
+    double c2acc[4] = {0.0, 0.0, 0.0, 0.0};
+    float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+    for (int i = tid; i < N; i += kLargeThreads) {
+      double a, b;
+      float af, bf;
+      load_global_sample<CT>(x + i, a, b, af, bf);
+      const double d = sqrt_nr(fma(a, a, b * b)) - mu_r;
+      const double d2 = d * d;
+      c2acc[0] += fabs(d);
+      c2acc[1] += d2;
+      c2acc[2] = fma(d2, d2, c2acc[2]);
+      const float p = phi[i];
+      const float e = p - mu_ph;
+      q2acc[0] = fmaf(e, e, q2acc[0]);
+      const float ea = fabsf(p) - mu_aph;
+      q2acc[1] = fmaf(ea, ea, q2acc[1]);
+      if (i < N - 1) {
+        float dd = phi[i + 1] - p;
+        const float over = fabsf(dd) - kPiF;
+        float fj;
+        if (fabsf(over) < kTieEps) {
+          fj = exact_freq_step<CT>(x, i);
+        } else {
+          if (over > 0.0f) dd -= copysignf(kTwoPiF, dd);
+          fj = dd * kInvTwoPiF;
+        }
+        const float ef = fj - mu_f;
+        const float ef2 = ef * ef;
+        q2acc[2] += ef2;
+        q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
+      }
+    }
+    warp_sum_multi<double, 4>(c2acc, lane);
+    warp_sum_multi<float, 4>(q2acc, lane);
+    if ((lane & 7) == 0) {
+      pw[20 + (lane >> 3)] = c2acc[0];                                   // 20..23 (23 unused)
+      pw[24 + (lane >> 3)] = static_cast<double>(q2acc[0]);              // 24..27
+    }
+
+    // ---------------------------------------------------------------- FFT: 16 x 16 x 16 x R4, in place
+    large_stage16<N, 1, Cfg::BPT>(buf, nullptr, tid);
+    large_stage16<N, 16, Cfg::BPT>(buf, g_tw_s2, tid);
+    large_stage16<N, 256, Cfg::BPT>(buf, g_tw_s3 + tw_s3_offset(4096), tid);
+    float vmax = 0.0f;
+    {
+      constexpr int R4 = Cfg::R4;                                        // last stage: N/R4 = 4096 butterflies
+#pragma unroll 2
+      for (int bb = 0; bb < 4096 / kLargeThreads; ++bb) {
+        const int j = tid + kLargeThreads * bb;
+        float2 u[R4];
+#pragma unroll
+        for (int q = 0; q < R4; ++q) u[q] = buf[swz16(j + 4096 * q)];
+#pragma unroll
+        for (int q = 1; q < R4; ++q) u[q] = c_mul(u[q], g_tw_l4[tw_l4_offset(N) + (q - 1) * 4096 + j]);
+        if constexpr (R4 == 2) {
+          bfly2(u[0], u[1]);
+        } else {
+          dft4(u[0], u[1], u[2], u[3]);
+        }
+#pragma unroll
+        for (int q = 0; q < R4; ++q) vmax = fmaxf(vmax, fmaf(u[q].x, u[q].x, u[q].y * u[q].y));
+      }
+    }
+    vmax = warp_max(vmax);
+    if (lane == 0) pw[28] = static_cast<double>(vmax);
+    __syncthreads();                                                     // totals complete; buf/phi free again
+
+    if (warp == 0) {                                                     // other warps start the next frame
+      double v = 0.0;
+      if (lane < 28) {
+#pragma unroll
+        for (int w = 0; w < kLargeWarps; ++w) v += pall[w * 32 + lane];
+      } else if (lane == 28) {
+#pragma unroll
+        for (int w = 0; w < kLargeWarps; ++w) v = fmax(v, pall[w * 32 + 28]);
+      }
+      FrameSums fs;
+#pragma unroll
+      for (int i = 0; i < 15; ++i) fs.mono[i] = __shfl_sync(FULL, v, i);
+      fs.sum_r = __shfl_sync(FULL, v, 15);
+      fs.mean_f = __shfl_sync(FULL, v, 18) / (N - 1);
+      fs.c_abs1 = __shfl_sync(FULL, v, 20);
+      fs.c2 = __shfl_sync(FULL, v, 21);
+      fs.c4 = __shfl_sync(FULL, v, 22);
+      fs.ph_m2 = __shfl_sync(FULL, v, 24);
+      fs.aph_m2 = __shfl_sync(FULL, v, 25);
+      fs.f_m2 = __shfl_sync(FULL, v, 26);
+      fs.f_m4 = __shfl_sync(FULL, v, 27);
+      fs.spec_max = __shfl_sync(FULL, v, 28);
+      if (lane == 0) finalize_features(fs, N, out + f * out_stride);
+    }
+  }
+}
+
+}  // namespace amc

@@ -26,8 +26,6 @@ dt = torch.complex128 if args.dtype == "c128" else torch.complex64
 g = torch.Generator(device="cuda").manual_seed(1)
 for n in args.sizes:
     frames = total // n
-    if n >= 8192:
-        frames = min(frames, 4096)          # general kernel: keep the run short
     x = torch.randn((frames, n), dtype=dt, device="cuda", generator=g)
     out = torch.empty((frames, 18), dtype=torch.float64, device="cuda")
     for _ in range(3):
