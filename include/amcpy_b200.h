@@ -25,9 +25,9 @@
  *
  * Layout contract: a "frame" is `frame_size` complex samples; frame f starts at element
  * f*frame_stride, sample n of it is at +n*sample_stride (strides in complex ELEMENTS).
- * The fused sm_100a kernel runs when sample_stride == 1, frame_size is one of
- * {256, 512, 1024, 2048, 4096} and every frame start is 16-byte aligned; every other shape
- * (any length >= 1, any strides) runs the general kernel.  Both run on the GPU; there is no CPU path.
+ * The fused sm_100a kernels run when sample_stride == 1, frame_size is one of
+ * {256, 512, 1024, 2048, 4096, 8192, 16384} and every frame start is 16-byte aligned; every other
+ * shape (any length >= 1, any strides) runs the general kernel.  All run on the GPU; there is no CPU path.
  *
  * Precision classes vs the reference on complex128 input (tests/ hold the tolerances):
  *   relative 1e-9 : features 4, 6, 7, 8 and 10..18 (float64 accumulation)
