@@ -100,10 +100,12 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
       s_aph += fabsf(ph[j]);
     }
     if (lane == 31) tie_mask &= ~(1u << (SPT - 1));
-    if (tie_mask != 0u) {
+    while (tie_mask != 0u) {   // rare (about once per 10^5 samples on noisy data); kept small: it sits inside the hot loop body
+      const int j = __ffs(tie_mask) - 1;
+      tie_mask &= tie_mask - 1u;
+      const float val = exact_freq_step<CT>(xs, lane + 32 * j);
 #pragma unroll
-      for (int j = 0; j < SPT; ++j)
-        if (tie_mask & (1u << j)) fq[j] = exact_freq_step<CT>(xs, lane + 32 * j);
+      for (int q = 0; q < SPT; ++q) fq[q] = (q == j) ? val : fq[q];
     }
     float s_f = 0.0f;
 #pragma unroll
