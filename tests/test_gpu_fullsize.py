@@ -143,3 +143,25 @@ def test_low_snr_frames_tie_redecision_statistics():
     want = orc.features_batch(x)
     got = ops.extract_features(torch.from_numpy(x).cuda()).cpu().numpy()
     assert_features_close(got, want)
+
+
+@pytest.mark.parametrize("n,frames", [(256, 60000), (1024, 12000), (2048, 48000), (4096, 3000), (16384, 600)])
+def test_repeated_launches_are_bitwise_identical(n, frames):
+    """Race detector of last resort (compute-sanitizer is closed on this pool): shared-memory
+    hazards in the barrier-light kernels would show up as run-to-run bit differences."""
+    import torch
+
+    from amcpy_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.randn((frames, n), dtype=torch.complex128, device="cuda", generator=g)
+    ref = ops.extract_features(x).clone()
+    s2 = torch.cuda.Stream()
+    for i in range(12):
+        if i % 3 == 2:     # also under concurrency with another stream running the same kernel
+            with torch.cuda.stream(s2):
+                other = ops.extract_features(x[: frames // 2])
+        got = ops.extract_features(x)
+        assert torch.equal(got, ref), f"launch {i} differs"
+    torch.cuda.synchronize()
+    assert torch.equal(other, ref[: frames // 2])

@@ -1,0 +1,17 @@
+"""Small invocation of every fused kernel for compute-sanitizer (one tool per gpurun call)."""
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch  # noqa: E402
+
+from amcpy_b200 import ops  # noqa: E402
+
+g = torch.Generator(device="cuda").manual_seed(1)
+for n, frames in ((2048, 700), (256, 3000), (512, 900), (1024, 500), (4096, 300), (8192, 200), (16384, 160)):
+    x = torch.randn((frames, n), dtype=torch.complex128, device="cuda", generator=g)
+    a = ops.extract_features(x)
+    torch.cuda.synchronize()
+    print(n, bool(torch.isfinite(a).all()))
+x = torch.randn((300, 2048), dtype=torch.complex64, device="cuda", generator=g)
+print("c64", bool(torch.isfinite(ops.extract_features(x)).all()))
