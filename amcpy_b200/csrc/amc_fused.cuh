@@ -1,4 +1,6 @@
-// Fused sm_100a kernel: all 18 features of a frame from ONE read of the frame out of HBM.
+// Fused sm_100a kernel, first generation (8 samples per thread): all 18 features of a frame from
+// ONE read of the frame out of HBM.  Superseded by amc_fused16.cuh / amc_fusedw.cuh / amc_large.cuh
+// (which reuse the building blocks defined here) and kept behind AMC_FLAG_FUSED_SPT8 for A/B runs.
 //
 //   * persistent CTAs; each "group" of N/8 threads owns one frame at a time (N=2048: 256 threads
 //     = the whole CTA; N=256: one warp per frame, 8 frames per CTA);
@@ -14,18 +16,6 @@
 #include "amc_device.cuh"
 
 namespace amc {
-
-constexpr int kTwN = 4096;                 // master twiddle table: W_4096^m, m in [0, 4096)
-__device__ float2 g_twiddle[kTwN];
-
-__global__ void init_twiddle_kernel() {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m < kTwN) {
-    double s, c;
-    sincospi(-2.0 * static_cast<double>(m) / kTwN, &s, &c);
-    g_twiddle[m] = make_float2(static_cast<float>(c), static_cast<float>(s));
-  }
-}
 
 // Lane-contiguous twiddle tables for the 8-samples-per-thread kernel (one or two 128-byte lines
 // per warp load instead of 8-32 with the generic table; see profiles/r1_experiments.txt):

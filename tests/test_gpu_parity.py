@@ -64,3 +64,13 @@ def test_ragged_and_large_frame_sizes(torch_cuda, n):
     x, want = golden_generic(n)
     got = ops.extract_features(torch_cuda.from_numpy(x).cuda()).cpu().numpy()
     assert_features_close(got, want)
+
+
+@pytest.mark.parametrize("n", [256, 1024, 2048, 4096])
+def test_first_generation_fused_kernel_still_in_parity(torch_cuda, n):
+    # AMC_FLAG_FUSED_SPT8: the 8-samples-per-thread kernel kept for A/B runs
+    from amcpy_b200 import ops
+
+    x, want = golden_frames(n)
+    got = ops.extract_features(torch_cuda.from_numpy(x).cuda(), spt8=True).cpu().numpy()
+    assert_features_close(got, want)
