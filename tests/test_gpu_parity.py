@@ -74,3 +74,24 @@ def test_first_generation_fused_kernel_still_in_parity(torch_cuda, n):
     x, want = golden_frames(n)
     got = ops.extract_features(torch_cuda.from_numpy(x).cuda(), spt8=True).cpu().numpy()
     assert_features_close(got, want)
+
+
+@pytest.mark.parametrize("n", [256, 2048, 16384])
+def test_exact_zeros_octant_points_and_signed_zero(torch_cuda, n):
+    """Samples that are exactly 0, on the axes / diagonals, or carry a negative zero: np.angle's
+    conventions (atan2 of signed zeros, exact octant values) and |x| = 0 must survive the fast paths."""
+    from amcpy_b200 import ops
+    from oracle import amc_oracle as orc
+
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((4, n)) + 1j * rng.standard_normal((4, n))) * 0.7
+    special = np.array([0 + 0j, 1 + 1j, -2 + 2j, -3 - 3j, 0.5 - 0.5j, 0 + 3j, 0 - 1j, -1 + 0j, 2 + 0j,
+                        complex(-0.0, 0.0), complex(-0.0, -0.0), complex(0.0, -0.0), complex(-1.0, -0.0)])
+    for r in range(4):
+        pos = rng.choice(n, size=n // 8, replace=False)
+        x[r, pos] = special[rng.integers(0, len(special), size=pos.size)]
+    x[3, : n // 2] = 0.0                                  # half of a frame exactly zero
+    want = orc.features_batch(x)
+    for force in (False, True):
+        got = ops.extract_features(torch_cuda.from_numpy(x).cuda(), force_general=force).cpu().numpy()
+        assert_features_close(got, want)
