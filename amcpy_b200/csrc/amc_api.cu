@@ -157,8 +157,9 @@ int launch_large(const void* iq, int64_t n_frames, int64_t frame_stride, double*
   using Cfg = amc::LargeCfg<N>;
   auto kern = amc::large_features_kernel<N, CT>;
   AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  const int grid = static_cast<int>(n_frames < sms ? n_frames : sms);
-  kern<<<grid, amc::kLargeThreads, Cfg::SMEM_BYTES, stream>>>(static_cast<const CT*>(iq), n_frames, frame_stride, out,
+  const int64_t cap = static_cast<int64_t>(sms) * Cfg::MIN_BLOCKS;
+  const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(static_cast<const CT*>(iq), n_frames, frame_stride, out,
                                                              out_stride);
   ++t_launches;
   AMC_CUDA(cudaGetLastError());

@@ -12,8 +12,6 @@
 
 namespace amc {
 
-constexpr int kLargeThreads = 512;
-constexpr int kLargeWarps = kLargeThreads / 32;
 
 // g_tw_l4[off(N) + q-1][j] = W_N^(j q), j < 4096, q = 1..N/4096-1
 __device__ float2 g_tw_l4[4 * 4096];
@@ -31,12 +29,15 @@ __global__ void init_twiddle_large_kernel() {
 template <int N>
 struct LargeCfg {
   static_assert(N == 8192 || N == 16384, "long-frame kernel sizes");
+  static constexpr int THREADS = N == 8192 ? 256 : 512;            // 8192: two CTAs per SM; 16384: one
+  static constexpr int WARPS = THREADS / 32;
+  static constexpr int MIN_BLOCKS = N == 8192 ? 2 : 1;
   static constexpr int FFT_BYTES = N * 8;
   static constexpr int PHI_BYTES = N * 4;
-  static constexpr int PART_BYTES = 2 * kLargeWarps * 32 * 8;      // two parities x 16 warps x 32 doubles
+  static constexpr int PART_BYTES = 2 * WARPS * 32 * 8;            // two parities x warps x 32 doubles
   static constexpr int SMEM_BYTES = FFT_BYTES + PHI_BYTES + PART_BYTES + 64;
   static constexpr int R4 = N / 4096;                              // radix of the last stage
-  static constexpr int BPT = (N / 16) / kLargeThreads;             // radix-16 butterflies per thread: 1 or 2
+  static constexpr int BPT = (N / 16) / THREADS;                   // radix-16 butterflies per thread: 2
 };
 
 template <typename CT>
@@ -45,19 +46,19 @@ __device__ __forceinline__ void load_global_sample(const CT* __restrict__ p, dou
 }
 
 // one in-place radix-16 Stockham stage over the whole frame (BPT butterflies per thread)
-template <int N, int NS, int BPT>
+template <int N, int NS, int BPT, int THREADS>
 __device__ __forceinline__ void large_stage16(float2* __restrict__ buf, const float2* __restrict__ tw, int tid) {
   float2 v[BPT][16];
 #pragma unroll
   for (int bb = 0; bb < BPT; ++bb) {
-    const int j = tid + kLargeThreads * bb;
+    const int j = tid + THREADS * bb;
 #pragma unroll
     for (int q = 0; q < 16; ++q) v[bb][q] = buf[swz16(j + (N / 16) * q)];
   }
   __syncthreads();                                                 // all reads of this stage are done
 #pragma unroll
   for (int bb = 0; bb < BPT; ++bb) {
-    const int j = tid + kLargeThreads * bb;
+    const int j = tid + THREADS * bb;
     const int k = j % NS;
     if constexpr (NS > 1) {
 #pragma unroll
@@ -72,10 +73,11 @@ __device__ __forceinline__ void large_stage16(float2* __restrict__ buf, const fl
 }
 
 template <int N, typename CT>
-__global__ void __launch_bounds__(kLargeThreads, 1)
+__global__ void __launch_bounds__(LargeCfg<N>::THREADS, LargeCfg<N>::MIN_BLOCKS)
 large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame_stride,
                       double* __restrict__ out, int64_t out_stride) {
   using Cfg = LargeCfg<N>;
+  constexpr int THREADS = Cfg::THREADS, WARPS = Cfg::WARPS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* buf = reinterpret_cast<float2*>(smem_raw);
   float* phi = reinterpret_cast<float*>(smem_raw + Cfg::FFT_BYTES);
@@ -86,8 +88,8 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
   int it = 0;
   for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x, ++it) {
     const CT* x = iq + f * frame_stride;
-    double* pw = part + ((it & 1) * kLargeWarps + warp) * 32;       // this warp's 32 partial slots
-    double* pall = part + (it & 1) * kLargeWarps * 32;
+    double* pw = part + ((it & 1) * WARPS + warp) * 32;       // this warp's 32 partial slots
+    double* pall = part + (it & 1) * WARPS * 32;
 
     // ---------------------------------------------------------------- pass 1
     Monomials mono;
@@ -95,7 +97,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     double sum_r = 0.0;
     float s_ph = 0.0f, s_aph = 0.0f;
 #pragma unroll 4
-    for (int i = tid; i < N; i += kLargeThreads) {
+    for (int i = tid; i < N; i += THREADS) {
       double a, b;
       float af, bf;
       load_global_sample<CT>(x + i, a, b, af, bf);
@@ -111,7 +113,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     // ---------------------------------------------------------------- pass 1b: sum of wrapped differences
     float s_f = 0.0f;
 #pragma unroll 4
-    for (int i = tid; i < N - 1; i += kLargeThreads) {
+    for (int i = tid; i < N - 1; i += THREADS) {
       float dd = phi[i + 1] - phi[i];
       const float over = fabsf(dd) - kPiF;
       float fj;
@@ -137,7 +139,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     __syncthreads();
     double tot_r = 0.0, tot_ph = 0.0, tot_aph = 0.0, tot_f = 0.0;
 #pragma unroll
-    for (int w = 0; w < kLargeWarps; ++w) {
+    for (int w = 0; w < WARPS; ++w) {
       tot_r += pall[w * 32 + 15];
       tot_ph += pall[w * 32 + 16];
       tot_aph += pall[w * 32 + 17];
@@ -151,7 +153,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     double c2acc[4] = {0.0, 0.0, 0.0, 0.0};
     float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 4
-    for (int i = tid; i < N; i += kLargeThreads) {
+    for (int i = tid; i < N; i += THREADS) {
       double a, b;
       float af, bf;
       load_global_sample<CT>(x + i, a, b, af, bf);
@@ -189,15 +191,15 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     }
 
     // ---------------------------------------------------------------- FFT: 16 x 16 x 16 x R4, in place
-    large_stage16<N, 1, Cfg::BPT>(buf, nullptr, tid);
-    large_stage16<N, 16, Cfg::BPT>(buf, g_tw_s2, tid);
-    large_stage16<N, 256, Cfg::BPT>(buf, g_tw_s3 + tw_s3_offset(4096), tid);
+    large_stage16<N, 1, Cfg::BPT, THREADS>(buf, nullptr, tid);
+    large_stage16<N, 16, Cfg::BPT, THREADS>(buf, g_tw_s2, tid);
+    large_stage16<N, 256, Cfg::BPT, THREADS>(buf, g_tw_s3 + tw_s3_offset(4096), tid);
     float vmax = 0.0f;
     {
       constexpr int R4 = Cfg::R4;                                        // last stage: N/R4 = 4096 butterflies
 #pragma unroll 2
-      for (int bb = 0; bb < 4096 / kLargeThreads; ++bb) {
-        const int j = tid + kLargeThreads * bb;
+      for (int bb = 0; bb < 4096 / THREADS; ++bb) {
+        const int j = tid + THREADS * bb;
         float2 u[R4];
 #pragma unroll
         for (int q = 0; q < R4; ++q) u[q] = buf[swz16(j + 4096 * q)];
@@ -220,10 +222,10 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
       double v = 0.0;
       if (lane < 28) {
 #pragma unroll
-        for (int w = 0; w < kLargeWarps; ++w) v += pall[w * 32 + lane];
+        for (int w = 0; w < WARPS; ++w) v += pall[w * 32 + lane];
       } else if (lane == 28) {
 #pragma unroll
-        for (int w = 0; w < kLargeWarps; ++w) v = fmax(v, pall[w * 32 + 28]);
+        for (int w = 0; w < WARPS; ++w) v = fmax(v, pall[w * 32 + 28]);
       }
       FrameSums fs;
 #pragma unroll
