@@ -65,9 +65,10 @@ int ensure_twiddles(int dev, cudaStream_t stream) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_tw_ready[dev]) return AMC_OK;
   amc::init_twiddle16_kernel<<<26, 256, 0, stream>>>();
+  amc::init_twiddle16dif_kernel<<<29, 256, 0, stream>>>();
   amc::init_twiddle8_kernel<<<22, 256, 0, stream>>>();
   amc::init_twiddle_large_kernel<<<64, 256, 0, stream>>>();
-  t_launches += 3;
+  t_launches += 4;
   AMC_CUDA(cudaGetLastError());
   AMC_CUDA(cudaStreamSynchronize(stream));  // once per device: later calls on other streams may rely on it
   g_tw_ready[dev] = true;

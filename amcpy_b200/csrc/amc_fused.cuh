@@ -91,6 +91,15 @@ __device__ __forceinline__ constexpr int out4(int r) { return ((r & 1) << 1) | (
 // (low 4 bits ^= [e4, e5, e6, e6]); reads of consecutive indices stay conflict-free.
 __device__ __forceinline__ int swz(int e) { return e ^ (((e >> 4) & 7) | (((e >> 6) & 1) << 3)); }
 
+// same decision, returned as the unwrapped phase step in radians (the fused16 kernel keeps frequency in radians)
+template <typename CT>
+__device__ __noinline__ float exact_phase_step(const CT* xs, int n) {
+  const CT v0 = xs[n], v1 = xs[n + 1];
+  const double p0 = atan2_exact(static_cast<double>(v0.y), static_cast<double>(v0.x));
+  const double p1 = atan2_exact(static_cast<double>(v1.y), static_cast<double>(v1.x));
+  return static_cast<float>(unwrap_step(p1 - p0));
+}
+
 template <int N, typename CT>
 struct FusedCfg {
   static constexpr int SPT = 8;                         // samples per thread

@@ -6,16 +6,17 @@
 //   * N/16 threads per frame (N=2048: 128 threads = one CTA, three CTAs per SM): every per-thread
 //     fixed cost (cross-lane reductions, partial stores, barriers, edge handling) is paid once per
 //     16 samples instead of once per 8;
-//   * FFT as radix 16 x 16 x (N/256): stage 1 straight from the registers of pass 1, only TWO
-//     shared-memory exchanges (was three), all exchange addresses are base + immediate after an
-//     XOR swizzle of the low four index bits;
+//   * FFT as radix 16 x 16 x (N/256), decimation in frequency: stage A (radix 16 over the 16 samples a
+//     thread already holds) straight from the registers of pass 1; ONE block-wide exchange hands
+//     each WARP complete (N/16)-point sub-transforms (512 points per warp), whose two stages
+//     exchange through a warp-private padded buffer with __syncwarp only;
 //   * the edge phase (first sample after each warp's run of 32) travels through 64 bytes of shared
 //     memory instead of one shuffle per sample;
 //   * the 18-feature finalisation is batched: warp 0 parks each frame's 25 totals in shared memory
 //     and finalises 16 frames at once, one lane per frame, instead of 32 redundant lanes per frame;
-//   * only TWO block barriers per frame: the FFT has its own two 16 KB buffers, so stage 1 (from
-//     registers) is written before the pass-1 barrier, the x slot is refilled by TMA right after
-//     that barrier, and a frame's totals are collected one frame later (double-buffered partials).
+//   * only ONE block barrier per frame: stage A is written before the pass-1 barrier, the x slot is
+//     refilled by TMA right after that barrier, everything after it is warp-local, and a frame's
+//     totals are collected one frame later (double-buffered partials).
 #pragma once
 #include "amc_fused.cuh"
 
@@ -79,15 +80,47 @@ __global__ void init_twiddle16_kernel() {
   }
 }
 
+// Twiddles of the decimation-in-frequency form used by fused16_features_kernel (lane-contiguous):
+//   g_tw_a[off_a(N)][k1-1][t]  = W_N^(t k1)        k1 = 1..15, t  = 0..N/16-1   (after stage A)
+//   g_tw_b[off_b(N)][q-1][m1]  = W_(N/16)^(m1 q)   q  = 1..15, m1 = 0..N/256-1  (after stage B)
+__device__ float2 g_tw_a[15 * (32 + 64 + 128 + 256)];
+__device__ float2 g_tw_b[15 * (2 + 4 + 8 + 16)];
+__host__ __device__ constexpr int tw_a_offset(int n) { return 15 * (n == 512 ? 0 : (n == 1024 ? 32 : (n == 2048 ? 96 : 224))); }
+__host__ __device__ constexpr int tw_b_offset(int n) { return 15 * (n == 512 ? 0 : (n == 1024 ? 2 : (n == 2048 ? 6 : 14))); }
+__global__ void init_twiddle16dif_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 15 * 480) {
+    int n = 512, rel = i;
+    while (rel >= 15 * (n / 16)) { rel -= 15 * (n / 16); n *= 2; }
+    const int grp = n / 16, k1 = rel / grp + 1, t = rel % grp;
+    double sn, cs;
+    sincospi(-2.0 * static_cast<double>(t * k1) / static_cast<double>(n), &sn, &cs);
+    g_tw_a[i] = make_float2(static_cast<float>(cs), static_cast<float>(sn));
+  }
+  if (i < 15 * 30) {
+    int n = 512, rel = i;
+    while (rel >= 15 * (n / 256)) { rel -= 15 * (n / 256); n *= 2; }
+    const int m1n = n / 256, q = rel / m1n + 1, m1 = rel % m1n;
+    double sn, cs;
+    sincospi(-2.0 * static_cast<double>(m1 * q) / static_cast<double>(n / 16), &sn, &cs);
+    g_tw_b[i] = make_float2(static_cast<float>(cs), static_cast<float>(sn));
+  }
+}
+
 // conflict-free exchange layout for the 16 x 16 x R Stockham passes: low 4 bits ^= bits 4..7
 __device__ __forceinline__ int swz16(int e) { return e ^ ((e >> 4) & 15); }
 
-#ifdef AMC_F16_INPLACE
-constexpr int kBatch = 8;         // (A/B build: in-place FFT buffer, 4 CTAs/SM at 128 registers)
-#else
-constexpr int kBatch = 16;        // frames finalised together (one lane each)
-#endif
+// Returns v, hidden from the optimiser when HIDE: values derived from it are recomputed where they are
+// used instead of being kept in (or spilled from) registers across the whole frame loop.
+template <bool HIDE>
+__device__ __forceinline__ int opaque_if(int v) {
+  if constexpr (HIDE) asm volatile("" : "+r"(v));
+  return v;
+}
+
 constexpr int kPendStride = 33;   // doubles per parked frame (32 + 1 pad: conflict-free lane-per-frame reads)
+constexpr int kTRow = 17;         // float2 per lane row of the warp-private exchange buffer (16 + 1 pad)
+constexpr int kPend16Stride = 25; // doubles per parked frame (25 totals; odd stride: conflict-free lane-per-frame reads)
 
 template <int N, typename CT>
 struct Fused16Cfg {
@@ -97,22 +130,25 @@ struct Fused16Cfg {
   static constexpr int G = CTA / GROUP;
   static constexpr int W = GROUP / 32;
   static constexpr int SLOT_BYTES = N * static_cast<int>(sizeof(CT));   // one x slot (TMA target)
-  static constexpr int FFT_BYTES = N * 8;                               // each of the two FFT buffers
+  static constexpr int FFT_BYTES = N * 8;                               // stage-A output, block-wide exchange
+  static constexpr int T_BYTES = W * 32 * kTRow * 8;                    // warp-private stage-B -> C exchange
   static constexpr int PART_D = 20, PART_F = 12;
   static constexpr int PART_BYTES = PART_D * 8 + PART_F * 4;            // 208 per (parity, warp)
   static constexpr int EDGE_BYTES = W * 16 * 4;
-  static constexpr int PEND_BYTES = 2 * kBatch * kPendStride * 8;       // 8448
-#ifdef AMC_F16_INPLACE
-  static constexpr int N_FFT_BUF = 1;
-#else
-  static constexpr int N_FFT_BUF = 2;
-#endif
-  static constexpr int GROUP_BYTES = SLOT_BYTES + N_FFT_BUF * FFT_BYTES + 2 * W * PART_BYTES + EDGE_BYTES + PEND_BYTES + 64;
+  static constexpr int BATCH = 32;                                      // frames finalised together, one lane each
+  static constexpr int PEND_BYTES = BATCH * kPend16Stride * 8;
+  static constexpr int RAW_BYTES = SLOT_BYTES + FFT_BYTES + T_BYTES + 2 * W * PART_BYTES + EDGE_BYTES + PEND_BYTES + 16;
+  static constexpr int GROUP_BYTES = (RAW_BYTES + 127) / 128 * 128;
+  static_assert(SLOT_BYTES % 128 == 0 && GROUP_BYTES % 128 == 0, "stage-A rows must stay 128-byte aligned (XOR addressing)");
   static constexpr int SMEM_BYTES = G * GROUP_BYTES;
   static constexpr int MIN_BLOCKS = (SMEM_BYTES <= 55 * 1024 && CTA <= 128) ? 4 : (SMEM_BYTES <= 75 * 1024) ? 3 : ((SMEM_BYTES <= 113 * 1024) ? 2 : 1);
-  static constexpr int R3 = N / 256;                     // radix of the last FFT stage: 2, 4, 8, 16
+  static constexpr bool REG_BOUND = MIN_BLOCKS >= 3 && CTA == 128;   // 168 registers per thread: see opaque_if
+  static constexpr int M1 = N / 256;                     // radix of the last FFT stage: 2, 4, 8, 16
+  static constexpr int LOG_M1 = M1 == 2 ? 1 : (M1 == 4 ? 2 : (M1 == 8 ? 3 : 4));
+  static constexpr int F = 32 / M1;                      // (N/16)-point sub-transforms per warp
   static_assert(N >= 512 && N <= 4096 && GROUP % 32 == 0, "frame size outside the 16-samples-per-thread kernel");
   static_assert(GROUP_BYTES % 16 == 0, "group region must keep 16-byte alignment");
+  static_assert(F * W == 16, "16 sub-transforms per frame");
 };
 
 template <int N, typename CT>
@@ -120,7 +156,7 @@ __global__ void __launch_bounds__(Fused16Cfg<N, CT>::CTA, Fused16Cfg<N, CT>::MIN
 fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame_stride,
                         double* __restrict__ out, int64_t out_stride) {
   using Cfg = Fused16Cfg<N, CT>;
-  constexpr int GROUP = Cfg::GROUP, W = Cfg::W, SPT = Cfg::SPT, R3 = Cfg::R3;
+  constexpr int GROUP = Cfg::GROUP, W = Cfg::W, SPT = Cfg::SPT, M1 = Cfg::M1, LOG_M1 = Cfg::LOG_M1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
 
   const int tid = threadIdx.x;
@@ -132,36 +168,40 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
   unsigned char* gbase = smem_raw + static_cast<size_t>(g) * Cfg::GROUP_BYTES;
   const CT* xs = reinterpret_cast<const CT*>(gbase);
   float2* buf_a = reinterpret_cast<float2*>(gbase + Cfg::SLOT_BYTES);
-  float2* buf_b = reinterpret_cast<float2*>(gbase + Cfg::SLOT_BYTES + (Cfg::N_FFT_BUF - 1) * Cfg::FFT_BYTES);
-  unsigned char* part_base = gbase + Cfg::SLOT_BYTES + Cfg::N_FFT_BUF * Cfg::FFT_BYTES;
+  float2* tbuf = reinterpret_cast<float2*>(gbase + Cfg::SLOT_BYTES + Cfg::FFT_BYTES) + wg * (32 * kTRow);
+  unsigned char* part_base = gbase + Cfg::SLOT_BYTES + Cfg::FFT_BYTES + Cfg::T_BYTES;
   float* edge_s = reinterpret_cast<float*>(part_base + 2 * W * Cfg::PART_BYTES) + wg * 16;
   double* pend = reinterpret_cast<double*>(part_base + 2 * W * Cfg::PART_BYTES + Cfg::EDGE_BYTES);
   uint64_t* bar = reinterpret_cast<uint64_t*>(part_base + 2 * W * Cfg::PART_BYTES + Cfg::EDGE_BYTES + Cfg::PEND_BYTES);
+  uint64_t* rbar = bar + 1;   // "every warp of the group has consumed the block-wide exchange + partials of a frame"
 
-  const int64_t gg = static_cast<int64_t>(blockIdx.x) * Cfg::G + g;
-  const int64_t tg = static_cast<int64_t>(gridDim.x) * Cfg::G;
-  const uint64_t policy = l2_evict_first_policy();
+  // (32-bit group ids and an L2 policy created at each use: the hot loop is register-bound and these
+  // values are only needed by one thread per frame)
+  const int gg = static_cast<int>(blockIdx.x) * Cfg::G + g;
+  const int tg = static_cast<int>(gridDim.x) * Cfg::G;
   // frames this group will process in total
   const int my_frames = (gg < n_frames) ? static_cast<int>((n_frames - gg + tg - 1) / tg) : 0;
 
   if (t == 0) {
     mbar_init(bar, 1);
+    mbar_init(rbar, W);
     fence_mbar_init();
   }
   __syncthreads();
+  if (lane == 0) mbar_arrive(rbar);   // phase 0 = "nothing to wait for" (keeps the wait in the loop unconditional)
   if (t == 0 && my_frames > 0) {
     mbar_arrive_expect_tx(bar, Cfg::SLOT_BYTES);
-    bulk_copy_g2s(gbase, iq + gg * frame_stride, Cfg::SLOT_BYTES, bar, policy);
+    bulk_copy_g2s(gbase, iq + static_cast<int64_t>(gg) * frame_stride, Cfg::SLOT_BYTES, bar, l2_evict_first_policy());
   }
 
   auto part_d = [&](int par, int w) { return reinterpret_cast<double*>(part_base + (par * W + w) * Cfg::PART_BYTES); };
   auto part_f = [&](int par, int w) {
     return reinterpret_cast<float*>(part_base + (par * W + w) * Cfg::PART_BYTES + Cfg::PART_D * 8);
   };
-  // warp 0: collect frame k's totals (25 values, lane i owns value i) and finalise 16 frames at a time
+  // warp 0: collect frame k's totals (25 values, lane i owns value i) and finalise up to 32 frames at a time
   auto park_and_finalize = [&](int k) {
-    const int par = k & 1, bi = k % kBatch, half = (k / kBatch) & 1;
-    double* pe = pend + (half * kBatch + bi) * kPendStride;
+    const int par = k & 1, bi = k % Cfg::BATCH;
+    double* pe = pend + bi * kPend16Stride;
     if (lane < 19) {
       double s = 0.0;
 #pragma unroll
@@ -169,16 +209,20 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       pe[lane] = s;
     } else if (lane < 25) {
       // 19..22 <- float sums 4..7 ; 23 <- sum f (float 2) ; 24 <- spectral max (float 8)
-      const int src = (lane < 23) ? (lane - 15) : (lane == 23 ? 2 : 8);
+      const int lp = opaque_if<Cfg::REG_BOUND>(lane);
+      const int src = (lp < 23) ? (lp - 15) : (lp == 23 ? 2 : 8);
       float s = part_f(par, 0)[src];
 #pragma unroll
       for (int w = 1; w < W; ++w) s = (lane == 24) ? fmaxf(s, part_f(par, w)[src]) : s + part_f(par, w)[src];
-      pe[lane] = static_cast<double>(s);
+      // frequency statistics were accumulated in radians: 21 <- /(2 pi)^2, 22 <- /(2 pi)^4, 23 <- /(2 pi)
+      constexpr double k1 = 0.15915494309189533577, k2 = k1 * k1;
+      const double sc = (lane == 21) ? k2 : (lane == 22 ? k2 * k2 : (lane == 23 ? k1 : 1.0));
+      pe[lane] = static_cast<double>(s) * sc;
     }
-    if (bi == kBatch - 1 || k == my_frames - 1) {
+    if (bi == Cfg::BATCH - 1 || k == my_frames - 1) {
       __syncwarp();
       if (lane <= bi) {
-        const double* pl = pend + (half * kBatch + lane) * kPendStride;
+        const double* pl = pend + lane * kPend16Stride;
         FrameSums fs;
 #pragma unroll
         for (int i = 0; i < 15; ++i) fs.mono[i] = pl[i];
@@ -199,10 +243,13 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     }
   };
 
-  // loop-invariant exchange offsets (float2 units)
-  const int tx = t & 15;
-  const int u0 = t ^ ((t >> 4) & 15);                 // swizzled position of element t (+ multiples of GROUP)
-  const int w2base = (t >> 4) * 256;                  // stage-2 output block of this thread
+  // loop-invariant exchange geometry (float2 units)
+  //   block-wide buffer: element (n1, k1) of stage A's output lives at n1*16 + (k1 ^ rot(n1 & 15)),
+  //   rot = rotate-left by 4 - log2(M1) inside 4 bits: conflict-free for the writers (fixed k1, 16
+  //   consecutive n1) and for the stage-B readers (fixed m2, lanes = (f, m1)).
+  //   (The per-lane addresses below are cheap functions of the thread index; they are recomputed in
+  //   every iteration from an opaque copy of it so that they do not occupy registers across pass 1,
+  //   where the kernel sits at its 168-register limit.)
 
   for (int it = 0; it < my_frames; ++it) {
     const int par = it & 1;
@@ -234,7 +281,8 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     }
     // phase of the sample after this warp's run of 32, for every j: lane j evaluates it, lane 31 uses it
     if (lane < SPT) {
-      const int idx = 32 * (wg + 1) + GROUP * lane;
+      const int te = opaque_if<Cfg::REG_BOUND>(t);
+      const int idx = 32 * ((te >> 5) + 1) + GROUP * (te & 31);
       float pe = 0.0f;
       if (idx < N) {
         double a, b;
@@ -247,9 +295,9 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     __syncwarp();
     // wrapped phase differences (np.unwrap); differences within kTieEps of +-pi are only flagged
     // here and re-decided in FP64 after the loop, so the hot loop stays branch-free
-    float fq[SPT];
+    float fq[SPT];                                             // unwrapped phase steps in RADIANS (scaled in park)
     float s_ph = 0.0f, s_aph = 0.0f;
-    unsigned tie_mask = 0u;
+    float tie_min = 1.0f;                                      // min | |dd| - pi | over this thread's steps
     const float last_keep = (t == GROUP - 1) ? 0.0f : 1.0f;   // sample N-1 has no successor
     float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -260,60 +308,91 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       if (lane == 31) nb = ej;
       float dd = nb - ph[j];
       const float over = fabsf(dd) - kPiF;
-      if (fabsf(over) < kTieEps) tie_mask |= 1u << j;
+      tie_min = fminf(tie_min, fabsf(over));
       if (over > 0.0f) dd -= copysignf(kTwoPiF, dd);
-      float fj = dd * kInvTwoPiF;
-      if (j == SPT - 1) fj *= last_keep;
-      fq[j] = fj;
+      if (j == SPT - 1) dd *= last_keep;
+      fq[j] = dd;
       s_ph += ph[j];
       s_aph += fabsf(ph[j]);
     }
-    if (t == GROUP - 1) tie_mask &= ~(1u << (SPT - 1));
-    while (tie_mask != 0u) {   // rare (about once per 10^5 samples on noisy data); kept small: it sits inside the hot loop body
-      const int j = __ffs(tie_mask) - 1;
-      tie_mask &= tie_mask - 1u;
-      const float val = exact_freq_step<CT>(xs, t + GROUP * j);
+    if (tie_min < kTieEps) {   // rare (about once per 10^5 samples on noisy data)
+      // a step whose raw difference was within kTieEps of +-pi ends up within kTieEps of +-pi after the
+      // wrap as well; re-deciding a few extra steps exactly is harmless.  (The step after sample N-1 was
+      // forced to 0 above and is never selected.)
+      unsigned tie_mask = 0u;
 #pragma unroll
-      for (int q = 0; q < SPT; ++q) fq[q] = (q == j) ? val : fq[q];
+      for (int j = 0; j < SPT; ++j)
+        if (fabsf(kPiF - fabsf(fq[j])) < 2.0f * kTieEps) tie_mask |= 1u << j;
+      while (tie_mask != 0u) {
+        const int j = __ffs(tie_mask) - 1;
+        tie_mask &= tie_mask - 1u;
+        const float val = exact_phase_step<CT>(xs, t + GROUP * j);
+#pragma unroll
+        for (int q = 0; q < SPT; ++q) fq[q] = (q == j) ? val : fq[q];
+      }
     }
     float s_f = 0.0f;
 #pragma unroll
     for (int j = 0; j < SPT; ++j) s_f += fq[j];
     {
-      double acc[16];
+      // 16 FP64 partials per lane -> 16 warp totals: transposed through the warp-private buffer
+      // (16 STS.64 + 16 LDS.64 + 16 DADD; the shuffle butterfly needed 60 selects + 32 shuffles)
+      double* red = reinterpret_cast<double*>(tbuf);
+      __syncwarp();                                     // stage C of the previous frame has read tbuf
 #pragma unroll
-      for (int i = 0; i < 15; ++i) acc[i] = mono.s[i];
-      acc[15] = sum_r;
-      warp_sum_multi<double, 16>(acc, lane);
+      for (int i = 0; i < 15; ++i) red[lane * kTRow + i] = mono.s[i];
+      red[lane * kTRow + 15] = sum_r;
       float accf[4] = {s_ph, s_aph, s_f, 0.0f};
       warp_sum_multi<float, 4>(accf, lane);
-      if ((lane & 1) == 0) part_d(par, wg)[lane >> 1] = acc[0];
+      __syncwarp();
+      const double* col = red + (lane >> 4) * (16 * kTRow) + (lane & 15);
+      double cs[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) cs[i] = col[i * kTRow];
+#pragma unroll
+      for (int w = 8; w >= 1; w >>= 1)                  // pairwise tree: same error growth as the butterfly
+#pragma unroll
+        for (int i = 0; i < w; ++i) cs[i] += cs[i + w];
+      const double tot = cs[0] + __shfl_xor_sync(0xffffffffu, cs[0], 16);
+      // every warp has finished reading the previous frame's stage-A output and (warp 0) the partials
+      // that are about to be overwritten; in steady state this completed long ago
+      mbar_wait(rbar, static_cast<uint32_t>(par));
+      if (lane < 16) part_d(par, wg)[lane] = tot;
       if ((lane & 7) == 0) part_f(par, wg)[lane >> 3] = accf[0];
     }
 
-    // ---------------------------------------------------------------- FFT stage 1 (Ns = 1), from registers
+    // ---------------------------------------------------------------- FFT stage A: radix 16 over this
+    // thread's own samples x[t + GROUP j] (registers), then the twiddle W_N^(t k1)
     float2 v[16];
-    float2 tw2[15];
+    const int tv = opaque_if<Cfg::REG_BOUND>(t);          // keeps the geometry below out of pass 1
+    const int lv = tv & 31, wv = tv >> 5;
 #ifndef AMC_EXP_NO_FFT
-#pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = make_float2(xr[q], xi[q]);
-    dft16(v);
     {
-      float2* row = buf_a + 16 * t;                       // element 16 t + q -> position q ^ (t & 15)
+      const int rot_t = (((tv & 15) << (4 - LOG_M1)) | ((tv & 15) >> LOG_M1)) & 15;
+      const uint32_t row_a = (smem_u32(buf_a) + 128u * tv) ^ (8u * rot_t);   // row start is 128-byte aligned
 #pragma unroll
-      for (int q = 0; q < 16; ++q) row[q ^ tx] = v[bitrev4(q)];
+      for (int q = 0; q < 16; ++q) v[q] = make_float2(xr[q], xi[q]);
+      dft16(v);
+      float2 tw[15];
+#pragma unroll
+      for (int q = 1; q < 16; ++q) tw[q - 1] = g_tw_a[tw_a_offset(N) + (q - 1) * GROUP + tv];   // 256 B per warp load
+#pragma unroll
+      for (int q = 1; q < 16; ++q) v[bitrev4(q)] = c_mul(v[bitrev4(q)], tw[q - 1]);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {   // element (t, q) -> row t, slot q ^ rot_t
+        const float2 o = v[bitrev4(q)];
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(row_a ^ (8u * q)), "f"(o.x), "f"(o.y) : "memory");
+      }
     }
-    // twiddles of the next stage are fetched BEFORE the barrier so their latency hides behind it
-#pragma unroll
-    for (int q = 1; q < 16; ++q) tw2[q - 1] = g_tw_s2[(q - 1) * 16 + tx];   // one 128-byte line per load
 #endif
 
-    group_sync<GROUP, Cfg::CTA>(g);   // (1) pass-1 partials + FFT stage-1 output visible; x slot fully read
+    group_sync<GROUP, Cfg::CTA>(g);   // THE barrier: pass-1 partials + stage-A output visible; x slot fully read
 
     if (t == 0 && it + 1 < my_frames) {                 // refill the x slot: frame it+1 streams in during pass 2 + FFT
       fence_proxy_async_smem();
       mbar_arrive_expect_tx(bar, Cfg::SLOT_BYTES);
-      bulk_copy_g2s(gbase, iq + (gg + static_cast<int64_t>(it + 1) * tg) * frame_stride, Cfg::SLOT_BYTES, bar, policy);
+      bulk_copy_g2s(gbase, iq + (gg + static_cast<int64_t>(it + 1) * tg) * frame_stride, Cfg::SLOT_BYTES, bar,
+                    l2_evict_first_policy());
     }
     if (wg == 0 && it > 0) park_and_finalize(it - 1);   // the previous frame's totals are complete now
 
@@ -328,7 +407,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     }
     const double mu_r = tot_r * (1.0 / N);
     const float mu_ph = tot_ph * (1.0f / N), mu_aph = tot_aph * (1.0f / N);
-    const float mu_f = tot_f * (1.0f / (N - 1));
+    const float mu_f = tot_f * (1.0f / (N - 1));       // radians
 
     // ---------------------------------------------------------------- pass 2 (registers only)
     {
@@ -362,54 +441,61 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     float vmax = 0.0f;
 #ifdef AMC_EXP_NO_FFT
     vmax = xr[0] + xi[15];
-    group_sync<GROUP, Cfg::CTA>(g);
 #else
-    // ---------------------------------------------------------------- FFT stage 2 (Ns = 16)
-    // element t + GROUP q ; (e >> 4) & 15 = (t >> 4) + (GROUP/16) q  (no carry)
-#pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = buf_a[(u0 ^ (((GROUP / 16) * q) & 15)) + GROUP * q];
-#pragma unroll
-    for (int q = 1; q < 16; ++q) v[q] = c_mul(v[q], tw2[q - 1]);
-    dft16(v);
-    if constexpr (Cfg::N_FFT_BUF == 1) group_sync<GROUP, Cfg::CTA>(g);   // in-place: every stage-2 read is done
+    // ---------------------------------------------------------------- FFT stage B: this warp owns the
+    // sub-transforms k1 = wg F .. wg F + F-1 (each GROUP points, n1 = m1 + M1 m2); lane (f, m1) does the
+    // radix-16 over m2 and applies W_GROUP^(m1 q)
+    float2* tb = reinterpret_cast<float2*>(gbase + Cfg::SLOT_BYTES + Cfg::FFT_BYTES) + wv * (32 * kTRow);
     {
-      // element 256 (t>>4) + 16 q + tx  ->  (e >> 4) & 15 = q
-      float2* blk = buf_b + w2base;
+      const int m1 = lv & (M1 - 1);
+      const int k1b = wv * Cfg::F + (lv >> LOG_M1);                  // sub-transform of this lane in stage B
+      const int kk_b = k1b ^ ((m1 << (4 - LOG_M1)) & 15);
+      float2* wr_t = tb + lv * kTRow;
+      float2 tw[15];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) blk[16 * q + (tx ^ q)] = v[bitrev4(q)];
-    }
-    group_sync<GROUP, Cfg::CTA>(g);   // (2) stage-2 output visible
-
-    // ---------------------------------------------------------------- FFT stage 3 (Ns = 256, last): radix R3
-#pragma unroll 1
-    for (int bb = 0; bb < 16 / R3; ++bb) {
-      const int jj = t + GROUP * bb;                      // 0..255
-      const int p0 = jj ^ ((jj >> 4) & 15);               // (e >> 4) & 15 = (jj >> 4) & 15 for e = jj + 256 q
-      float2 u[R3], w3[R3 - 1];
+      for (int q = 1; q < 16; ++q) tw[q - 1] = g_tw_b[tw_b_offset(N) + (q - 1) * M1 + m1];
 #pragma unroll
-      for (int q = 1; q < R3; ++q) w3[q - 1] = g_tw_s3[tw_s3_offset(N) + (q - 1) * 256 + jj];
-#pragma unroll
-      for (int q = 0; q < R3; ++q) u[q] = buf_b[p0 + 256 * q];
-#pragma unroll
-      for (int q = 1; q < R3; ++q) u[q] = c_mul(u[q], w3[q - 1]);
-      if constexpr (R3 == 2) {
-        bfly2(u[0], u[1]);
-      } else if constexpr (R3 == 4) {
-        dft4(u[0], u[1], u[2], u[3]);
-      } else if constexpr (R3 == 8) {
-        float2(&u8)[8] = reinterpret_cast<float2(&)[8]>(u);
-        dft8(u8);
-      } else {
-        float2(&u16)[16] = reinterpret_cast<float2(&)[16]>(u);
-        dft16(u16);
+      for (int m2 = 0; m2 < 16; ++m2) {
+        // (n1 & 15) = m1 + M1 (m2 mod 16/M1): the rotated swizzle is base ^ (m2 mod 16/M1)
+        v[m2] = buf_a[m1 * 16 + (kk_b ^ (m2 & (16 / M1 - 1))) + 16 * M1 * m2];
       }
+      dft16(v);
 #pragma unroll
-      for (int q = 0; q < R3; ++q) vmax = fmaxf(vmax, fmaf(u[q].x, u[q].x, u[q].y * u[q].y));
+      for (int q = 1; q < 16; ++q) v[bitrev4(q)] = c_mul(v[bitrev4(q)], tw[q - 1]);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) wr_t[q] = v[bitrev4(q)];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(rbar);   // this warp's reads of buf_a (and warp 0's parked partials) are done
+    // ---------------------------------------------------------------- FFT stage C (last): radix M1 over m1,
+    // 16 / M1 butterflies per lane, no twiddles; only max |X_k|^2 is kept
+    {
+      const float2* rd = tb + (lv >> 4) * (M1 * kTRow) + (lv & 15);
+#pragma unroll 1
+      for (int bb = 0; bb < 16 / M1; ++bb, rd += 2 * M1 * kTRow) {
+        float2 u[M1];
+#pragma unroll
+        for (int q = 0; q < M1; ++q) u[q] = rd[q * kTRow];
+        if constexpr (M1 == 2) {
+          bfly2(u[0], u[1]);
+        } else if constexpr (M1 == 4) {
+          dft4(u[0], u[1], u[2], u[3]);
+        } else if constexpr (M1 == 8) {
+          float2(&u8)[8] = reinterpret_cast<float2(&)[8]>(u);
+          dft8(u8);
+        } else {
+          float2(&u16)[16] = reinterpret_cast<float2(&)[16]>(u);
+          dft16(u16);
+        }
+#pragma unroll
+        for (int q = 0; q < M1; ++q) vmax = fmaxf(vmax, fmaf(u[q].x, u[q].x, u[q].y * u[q].y));
+      }
     }
 #endif
     vmax = warp_max(vmax);
     if (lane == 0) part_f(par, wg)[8] = vmax;
-    // no barrier here: buf_b / the partial arrays of this parity are next written two barriers later
+    // no barrier here: buf_a and the partial arrays are protected by rbar (waited on in the next frame's
+    // pass 1); the warp-private buffer is only touched by this warp
   }
 
   if (my_frames > 0) {                                  // (uniform per group)
