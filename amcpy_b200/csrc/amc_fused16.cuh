@@ -132,8 +132,10 @@ struct Fused16Cfg {
   static constexpr int SLOT_BYTES = N * static_cast<int>(sizeof(CT));   // one x slot (TMA target)
   static constexpr int FFT_BYTES = N * 8;                               // stage-A output, block-wide exchange
   static constexpr int T_BYTES = W * 32 * kTRow * 8;                    // warp-private stage-B -> C exchange
-  static constexpr int PART_D = 20, PART_F = 12;
-  static constexpr int PART_BYTES = PART_D * 8 + PART_F * 4;            // 208 per (parity, warp)
+  // per (parity, warp): the 25 frame totals as doubles (index = FrameSums order, see park_and_finalize)
+  // + the three pass-1 float sums every thread needs right after the barrier (phi, |phi|, f) + pad
+  static constexpr int PART_D = 25, PART_F = 4;
+  static constexpr int PART_BYTES = PART_D * 8 + PART_F * 4;            // 216 per (parity, warp)
   static constexpr int EDGE_BYTES = W * 16 * 4;
   static constexpr int BATCH = 32;                                      // frames finalised together, one lane each
   static constexpr int PEND_BYTES = BATCH * kPend16Stride * 8;
@@ -141,7 +143,11 @@ struct Fused16Cfg {
   static constexpr int GROUP_BYTES = (RAW_BYTES + 127) / 128 * 128;
   static_assert(SLOT_BYTES % 128 == 0 && GROUP_BYTES % 128 == 0, "stage-A rows must stay 128-byte aligned (XOR addressing)");
   static constexpr int SMEM_BYTES = G * GROUP_BYTES;
+#ifdef AMC_EXP_2CTA
+  static constexpr int MIN_BLOCKS = (SMEM_BYTES <= 113 * 1024) ? 2 : 1;
+#else
   static constexpr int MIN_BLOCKS = (SMEM_BYTES <= 55 * 1024 && CTA <= 128) ? 4 : (SMEM_BYTES <= 75 * 1024) ? 3 : ((SMEM_BYTES <= 113 * 1024) ? 2 : 1);
+#endif
   static constexpr bool REG_BOUND = MIN_BLOCKS >= 3 && CTA == 128;   // 168 registers per thread: see opaque_if
   static constexpr int M1 = N / 256;                     // radix of the last FFT stage: 2, 4, 8, 16
   static constexpr int LOG_M1 = M1 == 2 ? 1 : (M1 == 4 ? 2 : (M1 == 8 ? 3 : 4));
@@ -198,26 +204,25 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
   auto part_f = [&](int par, int w) {
     return reinterpret_cast<float*>(part_base + (par * W + w) * Cfg::PART_BYTES + Cfg::PART_D * 8);
   };
-  // warp 0: collect frame k's totals (25 values, lane i owns value i) and finalise up to 32 frames at a time
+  // warp 0: collect frame k's totals (25 values, lane i owns value i) and finalise up to 32 frames at a time.
+  // Values: 0..14 monomial sums, 15 sum|x|, 16 sum|r-mu|, (17 unused,) 18 sum (r-mu)^4, 19 sum (phi-mu)^2,
+  // 20 sum (|phi|-mu)^2, 21/22 sum (f-mu)^2/^4, 23 sum f, 24 max|X|^2.  Frequency sums were accumulated in
+  // radians: 21 <- /(2 pi)^2, 22 <- /(2 pi)^4, 23 <- /(2 pi).
   auto park_and_finalize = [&](int k) {
     const int par = k & 1, bi = k % Cfg::BATCH;
     double* pe = pend + bi * kPend16Stride;
-    if (lane < 19) {
-      double s = 0.0;
+    if (lane < 25) {
+      double s = part_d(par, 0)[lane];
+      if (lane == 24) {
 #pragma unroll
-      for (int w = 0; w < W; ++w) s += part_d(par, w)[lane];
-      pe[lane] = s;
-    } else if (lane < 25) {
-      // 19..22 <- float sums 4..7 ; 23 <- sum f (float 2) ; 24 <- spectral max (float 8)
-      const int lp = opaque_if<Cfg::REG_BOUND>(lane);
-      const int src = (lp < 23) ? (lp - 15) : (lp == 23 ? 2 : 8);
-      float s = part_f(par, 0)[src];
+        for (int w = 1; w < W; ++w) s = fmax(s, part_d(par, w)[lane]);
+      } else {
 #pragma unroll
-      for (int w = 1; w < W; ++w) s = (lane == 24) ? fmaxf(s, part_f(par, w)[src]) : s + part_f(par, w)[src];
-      // frequency statistics were accumulated in radians: 21 <- /(2 pi)^2, 22 <- /(2 pi)^4, 23 <- /(2 pi)
+        for (int w = 1; w < W; ++w) s += part_d(par, w)[lane];
+      }
       constexpr double k1 = 0.15915494309189533577, k2 = k1 * k1;
-      const double sc = (lane == 21) ? k2 : (lane == 22 ? k2 * k2 : (lane == 23 ? k1 : 1.0));
-      pe[lane] = static_cast<double>(s) * sc;
+      if (lane >= 21 && lane <= 23) s *= (lane == 21) ? k2 : (lane == 22 ? k2 * k2 : k1);
+      pe[lane] = s;
     }
     if (bi == Cfg::BATCH - 1 || k == my_frames - 1) {
       __syncwarp();
@@ -228,7 +233,9 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         for (int i = 0; i < 15; ++i) fs.mono[i] = pl[i];
         fs.sum_r = pl[15];
         fs.c_abs1 = pl[16];
-        fs.c2 = pl[17];
+        // sum (r-mu)^2 = sum |x|^2 - (sum |x|)^2 / N: the cancellation costs (mu/sigma)^2 ulps (< 1e-11
+        // relative even at 40 dB SNR), and saves one FP64 add per sample in pass 2
+        fs.c2 = (pl[0] + pl[1]) - pl[15] * pl[15] * (1.0 / N);
         fs.c4 = pl[18];
         fs.ph_m2 = pl[19];
         fs.aph_m2 = pl[20];
@@ -358,7 +365,8 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       // that are about to be overwritten; in steady state this completed long ago
       mbar_wait(rbar, static_cast<uint32_t>(par));
       if (lane < 16) part_d(par, wg)[lane] = tot;
-      if ((lane & 7) == 0) part_f(par, wg)[lane >> 3] = accf[0];
+      if ((lane & 7) == 0 && lane < 24) part_f(par, wg)[lane >> 3] = accf[0];
+      if (lane == 16) part_d(par, wg)[23] = static_cast<double>(accf[0]);   // sum f, again, for the finalisation
     }
 
     // ---------------------------------------------------------------- FFT stage A: radix 16 over this
@@ -411,15 +419,14 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
 
     // ---------------------------------------------------------------- pass 2 (registers only)
     {
-      double c2acc[4] = {0.0, 0.0, 0.0, 0.0};
+      double c2acc[2] = {0.0, 0.0};                      // sum |r-mu|, sum (r-mu)^4
       float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int j = 0; j < SPT; ++j) {
         const double d = r[j] - mu_r;
         const double d2 = d * d;
         c2acc[0] += fabs(d);
-        c2acc[1] += d2;
-        c2acc[2] = fma(d2, d2, c2acc[2]);
+        c2acc[1] = fma(d2, d2, c2acc[1]);
         const float e = ph[j] - mu_ph;
         q2acc[0] = fmaf(e, e, q2acc[0]);
         const float ea = fabsf(ph[j]) - mu_aph;
@@ -430,12 +437,10 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         q2acc[2] += ef2;
         q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
       }
-      warp_sum_multi<double, 4>(c2acc, lane);
+      warp_sum_multi<double, 2>(c2acc, lane);            // lanes 0..15: sum |r-mu| ; 16..31: sum (r-mu)^4
       warp_sum_multi<float, 4>(q2acc, lane);
-      if ((lane & 7) == 0) {
-        part_d(par, wg)[16 + (lane >> 3)] = c2acc[0];
-        part_f(par, wg)[4 + (lane >> 3)] = q2acc[0];
-      }
+      if ((lane & 15) == 0) part_d(par, wg)[16 + (lane >> 3)] = c2acc[0];   // -> 16 and 18 (17 is derived)
+      if ((lane & 7) == 0) part_d(par, wg)[19 + (lane >> 3)] = static_cast<double>(q2acc[0]);
     }
 
     float vmax = 0.0f;
@@ -493,7 +498,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     }
 #endif
     vmax = warp_max(vmax);
-    if (lane == 0) part_f(par, wg)[8] = vmax;
+    if (lane == 0) part_d(par, wg)[24] = static_cast<double>(vmax);
     // no barrier here: buf_a and the partial arrays are protected by rbar (waited on in the next frame's
     // pass 1); the warp-private buffer is only touched by this warp
   }
