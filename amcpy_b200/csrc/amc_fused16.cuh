@@ -118,7 +118,6 @@ __device__ __forceinline__ int opaque_if(int v) {
   return v;
 }
 
-constexpr int kPendStride = 33;   // doubles per parked frame (32 + 1 pad: conflict-free lane-per-frame reads)
 constexpr int kTRow = 17;         // float2 per lane row of the warp-private exchange buffer (16 + 1 pad)
 constexpr int kPend16Stride = 25; // doubles per parked frame (25 totals; odd stride: conflict-free lane-per-frame reads)
 

@@ -3,12 +3,16 @@
 // barrier at all (only __syncwarp), the neighbour phase of lane 31 is lane 0's next sample (one
 // rotating shuffle, no edge re-evaluation), totals are parked per warp and finalised eight frames
 // at a time with one lane per frame.  FFT: radix 8 x 8 x 4 through the frame's own TMA slot.
+// The 16 FP64 partials per lane are summed through a warp-private padded transposition buffer
+// (16 STS.64 + 16 LDS.64 + 16 DADD instead of a 60-select / 32-shuffle butterfly).
 #pragma once
 #include "amc_fused.cuh"
 
 namespace amc {
 
 constexpr int kWBatch = 8;
+constexpr int kWPendStride = 25;   // doubles per parked frame (odd: conflict-free lane-per-frame reads)
+constexpr int kWRow = 17;          // doubles per lane row of the reduction buffer (16 + 1 pad)
 
 template <int N, typename CT>
 struct FusedWCfg {
@@ -18,8 +22,9 @@ struct FusedWCfg {
   static constexpr int SLOT_BYTES = N * static_cast<int>(sizeof(CT));
   static constexpr bool C128 = sizeof(CT) == 16;
   static constexpr int FFTB_BYTES = C128 ? 0 : N * 8;        // c128: both FFT buffers live in the slot
-  static constexpr int PEND_BYTES = kWBatch * kPendStride * 8;
-  static constexpr int GROUP_BYTES = 2 * SLOT_BYTES + FFTB_BYTES + PEND_BYTES + 64;
+  static constexpr int PEND_BYTES = kWBatch * kWPendStride * 8;
+  static constexpr int RED_BYTES = 32 * kWRow * 8;
+  static constexpr int GROUP_BYTES = 2 * SLOT_BYTES + FFTB_BYTES + PEND_BYTES + RED_BYTES + 64;
   static constexpr int SMEM_BYTES = G * GROUP_BYTES;
   static_assert(GROUP_BYTES % 16 == 0, "group region must keep 16-byte alignment");
 };
@@ -38,7 +43,9 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
   unsigned char* gbase = smem_raw + static_cast<size_t>(g) * Cfg::GROUP_BYTES;
   float2* fft_b_extra = reinterpret_cast<float2*>(gbase + 2 * Cfg::SLOT_BYTES);
   double* pend = reinterpret_cast<double*>(gbase + 2 * Cfg::SLOT_BYTES + Cfg::FFTB_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + 2 * Cfg::SLOT_BYTES + Cfg::FFTB_BYTES + Cfg::PEND_BYTES);
+  double* red = reinterpret_cast<double*>(gbase + 2 * Cfg::SLOT_BYTES + Cfg::FFTB_BYTES + Cfg::PEND_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + 2 * Cfg::SLOT_BYTES + Cfg::FFTB_BYTES + Cfg::PEND_BYTES +
+                                               Cfg::RED_BYTES);
 
   const int64_t gg = static_cast<int64_t>(blockIdx.x) * Cfg::G + g;
   const int64_t tg = static_cast<int64_t>(gridDim.x) * Cfg::G;
@@ -80,9 +87,9 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
       sum_r = (j == 0) ? r[j] : sum_r + r[j];
       ph[j] = atan2_fast(xi[j], xr[j]);
     }
-    float fq[SPT];
+    float fq[SPT];                                            // unwrapped phase steps in RADIANS (scaled when parked)
     float s_ph = 0.0f, s_aph = 0.0f;
-    unsigned tie_mask = 0u;
+    float tie_min = 1.0f;                                     // min | |dd| - pi | over this lane's steps
     const float last_keep = (lane == 31) ? 0.0f : 1.0f;       // sample N-1 has no successor
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
@@ -91,49 +98,65 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
       const float nb = __shfl_sync(FULL, offer, (lane + 1) & 31);
       float dd = nb - ph[j];
       const float over = fabsf(dd) - kPiF;
-      if (fabsf(over) < kTieEps) tie_mask |= 1u << j;
+      tie_min = fminf(tie_min, fabsf(over));
       if (over > 0.0f) dd -= copysignf(kTwoPiF, dd);
-      float fj = dd * kInvTwoPiF;
-      if (j == SPT - 1) fj *= last_keep;
-      fq[j] = fj;
+      if (j == SPT - 1) dd *= last_keep;
+      fq[j] = dd;
       s_ph += ph[j];
       s_aph += fabsf(ph[j]);
     }
-    if (lane == 31) tie_mask &= ~(1u << (SPT - 1));
-    while (tie_mask != 0u) {   // rare (about once per 10^5 samples on noisy data); kept small: it sits inside the hot loop body
-      const int j = __ffs(tie_mask) - 1;
-      tie_mask &= tie_mask - 1u;
-      const float val = exact_freq_step<CT>(xs, lane + 32 * j);
+    if (tie_min < kTieEps) {   // rare (about once per 10^5 samples on noisy data): FP64 re-decision, see amc_fused16.cuh
+      unsigned tie_mask = 0u;
 #pragma unroll
-      for (int q = 0; q < SPT; ++q) fq[q] = (q == j) ? val : fq[q];
+      for (int j = 0; j < SPT; ++j)
+        if (fabsf(kPiF - fabsf(fq[j])) < 2.0f * kTieEps) tie_mask |= 1u << j;
+      while (tie_mask != 0u) {
+        const int j = __ffs(tie_mask) - 1;
+        tie_mask &= tie_mask - 1u;
+        const float val = exact_phase_step<CT>(xs, lane + 32 * j);
+#pragma unroll
+        for (int q = 0; q < SPT; ++q) fq[q] = (q == j) ? val : fq[q];
+      }
     }
     float s_f = 0.0f;
 #pragma unroll
     for (int j = 0; j < SPT; ++j) s_f += fq[j];
 
-    double acc[16];
+    // 16 FP64 partials per lane -> lane l (and l + 16) holds the warp total of value l
+    __syncwarp();                                             // the previous frame's column reads are done
 #pragma unroll
-    for (int i = 0; i < 15; ++i) acc[i] = mono.s[i];
-    acc[15] = sum_r;
-    warp_sum_multi<double, 16>(acc, lane);                    // lane l: total of value l >> 1
+    for (int i = 0; i < 15; ++i) red[lane * kWRow + i] = mono.s[i];
+    red[lane * kWRow + 15] = sum_r;
     float accf[4] = {s_ph, s_aph, s_f, 0.0f};
     warp_sum_multi<float, 4>(accf, lane);                     // lane l: total of value l >> 3
-    const double mu_r = __shfl_sync(FULL, acc[0], 30) * (1.0 / N);
+    __syncwarp();
+    double tot16;
+    {
+      const double* col = red + (lane >> 4) * (16 * kWRow) + (lane & 15);
+      double cs[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) cs[i] = col[i * kWRow];
+#pragma unroll
+      for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+        for (int i = 0; i < w; ++i) cs[i] += cs[i + w];
+      tot16 = cs[0] + __shfl_xor_sync(FULL, cs[0], 16);
+    }
+    const double mu_r = __shfl_sync(FULL, tot16, 15) * (1.0 / N);
     const float mu_ph = __shfl_sync(FULL, accf[0], 0) * (1.0f / N);
     const float mu_aph = __shfl_sync(FULL, accf[0], 8) * (1.0f / N);
     const float tot_f = __shfl_sync(FULL, accf[0], 16);
-    const float mu_f = tot_f * (1.0f / (N - 1));
+    const float mu_f = tot_f * (1.0f / (N - 1));              // radians
 
     // ---------------------------------------------------------------- pass 2 (registers only)
-    double c2acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double c2acc[2] = {0.0, 0.0};                             // sum |r-mu|, sum (r-mu)^4 (sum (r-mu)^2 is derived)
     float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
       const double d = r[j] - mu_r;
       const double d2 = d * d;
       c2acc[0] += fabs(d);
-      c2acc[1] += d2;
-      c2acc[2] = fma(d2, d2, c2acc[2]);
+      c2acc[1] = fma(d2, d2, c2acc[1]);
       const float e = ph[j] - mu_ph;
       q2acc[0] = fmaf(e, e, q2acc[0]);
       const float ea = fabsf(ph[j]) - mu_aph;
@@ -144,7 +167,7 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
       q2acc[2] += ef2;
       q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
     }
-    warp_sum_multi<double, 4>(c2acc, lane);                   // lane l: value l >> 3
+    warp_sum_multi<double, 2>(c2acc, lane);                   // lane l: value l >> 4
     warp_sum_multi<float, 4>(q2acc, lane);
 
     // ---------------------------------------------------------------- FFT 8 x 8 x 4 through the slot
@@ -195,24 +218,26 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
 
     // ---------------------------------------------------------------- park this frame's 25 totals
     const int bi = it % kWBatch;
-    double* pe = pend + bi * kPendStride;
-    if ((lane & 1) == 0) pe[lane >> 1] = acc[0];                       // 0..15
-    if ((lane & 7) == 0) {
-      if ((lane >> 3) < 3) pe[16 + (lane >> 3)] = c2acc[0];            // 16..18
-      pe[19 + (lane >> 3)] = static_cast<double>(q2acc[0]);            // 19..22
+    double* pe = pend + bi * kWPendStride;
+    constexpr double kInv2Pi = 0.15915494309189533577, kInv2Pi2 = kInv2Pi * kInv2Pi;
+    if (lane < 16) pe[lane] = tot16;                                   // 0..15
+    if ((lane & 15) == 0) pe[16 + (lane >> 3)] = c2acc[0];             // 16 and 18 (17 is derived)
+    if ((lane & 7) == 0) {                                             // 19..22; frequency sums: radians -> cycles
+      const double sc = (lane == 16) ? kInv2Pi2 : (lane == 24 ? kInv2Pi2 * kInv2Pi2 : 1.0);
+      pe[19 + (lane >> 3)] = static_cast<double>(q2acc[0]) * sc;
     }
-    if (lane == 1) pe[23] = static_cast<double>(tot_f);
+    if (lane == 1) pe[23] = static_cast<double>(tot_f) * kInv2Pi;
     if (lane == 3) pe[24] = static_cast<double>(vmax);
     if (bi == kWBatch - 1 || it == my_frames - 1) {
       __syncwarp();
       if (lane <= bi) {
-        const double* pl = pend + lane * kPendStride;
+        const double* pl = pend + lane * kWPendStride;
         FrameSums fs;
 #pragma unroll
         for (int i = 0; i < 15; ++i) fs.mono[i] = pl[i];
         fs.sum_r = pl[15];
         fs.c_abs1 = pl[16];
-        fs.c2 = pl[17];
+        fs.c2 = (pl[0] + pl[1]) - pl[15] * pl[15] * (1.0 / N);   // sum (r-mu)^2 from the raw sums
         fs.c4 = pl[18];
         fs.ph_m2 = pl[19];
         fs.aph_m2 = pl[20];
