@@ -5,8 +5,11 @@ Frames are independent units (each frame's 18 outputs depend on that frame only 
 (snr, frame) as independent work items - feature_extraction.py:64-72, :89-92), so the flattened
 (modulation, snr, frame) index space is cut into one contiguous range per rank and there is NO
 collective on the data path.  The only exchange is the optional gather of the (frames, 18) feature
-matrix to every rank / rank 0 for the downstream classifier (NCCL over NVLink on GPUs, gloo in the
-CPU tests).
+matrix to every rank / rank 0 for the downstream classifier:
+  * `gather_features`          - NCCL `all_gather_into_tensor` over NVLink (gloo in the CPU tests);
+  * `extract_sharded_to_root`  - no collective call at all: every rank's extraction kernel stores its
+    144-byte rows straight into the root's matrix through the NVLink/NVSwitch peer mapping of a
+    symmetric-memory buffer, so the gather rides on the kernel's own epilogue.
 """
 
 from __future__ import annotations
@@ -61,3 +64,38 @@ def extract_sharded(frames_local, total: int, gather: bool = True, group=None):
 
     local = ops.extract_features(frames_local)
     return gather_features(local, total, group) if gather else local
+
+
+_SYMM_CACHE: dict = {}
+
+
+def extract_sharded_to_root(frames_local, total: int, root: int = 0, group=None):
+    """Features of this rank's shard, written by the extraction kernel DIRECTLY into `root`'s
+    (total, 18) matrix over NVLink (peer stores into a torch symmetric-memory buffer).
+
+    The kernel's finalisation stores each frame's 144-byte row to `out`; here `out` is the peer
+    mapping of the root's buffer at this rank's row offset, so compute and gather are one kernel and
+    the only extra work is one device-side barrier.  Returns the (total, 18) float64 tensor on
+    `root` (valid after the call in stream order) and None on the other ranks.  NCCL/CUDA only."""
+    import torch
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm
+
+    from . import ops
+
+    group = group if group is not None else dist.group.WORLD
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_range(total, rank, world)
+    if frames_local.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank}: {frames_local.shape[0]} local frames, shard is [{lo},{hi})")
+    key = (total, frames_local.device.index, group.group_name)
+    if key not in _SYMM_CACHE:   # allocation + rendezvous are collective and slow: once per shape
+        buf = symm.empty((total, ops.N_FEATURES), dtype=torch.float64, device=frames_local.device)
+        _SYMM_CACHE[key] = (buf, symm.rendezvous(buf, group))
+    buf, hdl = _SYMM_CACHE[key]
+    dst = hdl.get_buffer(root, (total, ops.N_FEATURES), torch.float64)   # root's buffer, peer-mapped here
+    hdl.barrier()                    # the root is done reading the previous result
+    if hi > lo:
+        ops.extract_features(frames_local, out=dst[lo:hi])
+    hdl.barrier()                    # every rank's rows have landed in the root's memory
+    return buf if rank == root else None
