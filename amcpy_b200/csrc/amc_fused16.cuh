@@ -142,7 +142,7 @@ struct Fused16Cfg {
   static constexpr int GROUP_BYTES = (RAW_BYTES + 127) / 128 * 128;
   static_assert(SLOT_BYTES % 128 == 0 && GROUP_BYTES % 128 == 0, "stage-A rows must stay 128-byte aligned (XOR addressing)");
   static constexpr int SMEM_BYTES = G * GROUP_BYTES;
-#ifdef AMC_EXP_2CTA
+#if defined(AMC_EXP_2CTA)
   static constexpr int MIN_BLOCKS = (SMEM_BYTES <= 113 * 1024) ? 2 : 1;
 #else
   static constexpr int MIN_BLOCKS = (SMEM_BYTES <= 55 * 1024 && CTA <= 128) ? 4 : (SMEM_BYTES <= 75 * 1024) ? 3 : ((SMEM_BYTES <= 113 * 1024) ? 2 : 1);
@@ -378,7 +378,14 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       const int rot_t = (((tv & 15) << (4 - LOG_M1)) | ((tv & 15) >> LOG_M1)) & 15;
       const uint32_t row_a = (smem_u32(buf_a) + 128u * tv) ^ (8u * rot_t);   // row start is 128-byte aligned
 #pragma unroll
+#ifdef AMC_EXP_RELOAD_X
+      for (int q = 0; q < 16; ++q) {                      // A/B: re-read x from the slot instead of keeping xr/xi live
+        double a, b;
+        load_sample<CT>(xs + tv + GROUP * q, a, b, v[q].x, v[q].y);
+      }
+#else
       for (int q = 0; q < 16; ++q) v[q] = make_float2(xr[q], xi[q]);
+#endif
       dft16(v);
       float2 tw[15];
 #pragma unroll
