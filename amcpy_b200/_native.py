@@ -122,3 +122,27 @@ def require_cuda() -> int:
     n = lib().amc_device_count()
     check(n)
     return n
+
+
+def bind_host_thread_to_gpu(device_index: int) -> list[int]:
+    """Pin the calling process to the CPUs NVML reports as local to `device_index` (its NUMA node), so
+    that pinned staging buffers allocated afterwards are first-touched next to that GPU's PCIe root.
+    With one rank per GPU on a two-socket host this is what keeps N ranks from sharing one socket's
+    memory controllers during host -> device streaming.  Best effort: returns the CPU list it set,
+    or [] when NVML / affinity are unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return []
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # noqa: BLE001 - affinity is an optimisation, never a requirement
+        return []

@@ -270,6 +270,15 @@ def run_cuda_arm(args):
         if rank == 0:
             print(json.dumps({"profiling_only": True, "kernel_ms_per_launch": kernel_ms, "value": value}), flush=True)
         return 0
+    # one rank per GPU: allocate (first-touch) the pinned staging buffers on the GPU's own NUMA node
+    physical = local_rank
+    if os.environ.get("CUDA_VISIBLE_DEVICES"):
+        try:
+            physical = int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])
+        except (ValueError, IndexError):
+            physical = local_rank
+    affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa_cpus = nat.bind_host_thread_to_gpu(physical)
     xh = torch.empty((n_frames, FRAME), dtype=torch.complex128, pin_memory=True)
     xh.copy_(x)
     oh = torch.empty((n_frames, 18), dtype=torch.float64, pin_memory=True)
@@ -287,6 +296,8 @@ def run_cuda_arm(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n_frames * e2e_steps / float(te.item())
     same = bool(torch.equal(torch.from_numpy(oh_np).to(dev), out))
+    if affinity0 is not None and numa_cpus:
+        os.sched_setaffinity(0, affinity0)   # the CPU baseline below uses every core of the box again
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -319,7 +330,7 @@ def run_cuda_arm(args):
                 "value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n_frames * FRAME * 16,
                 "d2h_bytes_per_step": n_frames * 18 * 8, "steps": e2e_steps,
                 "api": "amcpy_b200.ops.extract_features_host -> C ABI amc_extract_host (pinned host buffers)",
-                "matches_device_path": same,
+                "matches_device_path": same, "host_cpus_bound": len(numa_cpus),
             },
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
