@@ -204,7 +204,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     return reinterpret_cast<float*>(part_base + (par * W + w) * Cfg::PART_BYTES + Cfg::PART_D * 8);
   };
   // warp 0: collect frame k's totals (25 values, lane i owns value i) and finalise up to 32 frames at a time.
-  // Values: 0..14 monomial sums, 15 sum|x|, 16 sum|r-mu|, (17 unused,) 18 sum (r-mu)^4, 19 sum (phi-mu)^2,
+  // Values: 0..14 monomial sums, 15 sum|x|, 16 sum|r-mu|, 17/18 sum (r-mu)^2/^4, 19 sum (phi-mu)^2,
   // 20 sum (|phi|-mu)^2, 21/22 sum (f-mu)^2/^4, 23 sum f, 24 max|X|^2.  Frequency sums were accumulated in
   // radians: 21 <- /(2 pi)^2, 22 <- /(2 pi)^4, 23 <- /(2 pi).
   auto park_and_finalize = [&](int k) {
@@ -232,9 +232,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         for (int i = 0; i < 15; ++i) fs.mono[i] = pl[i];
         fs.sum_r = pl[15];
         fs.c_abs1 = pl[16];
-        // sum (r-mu)^2 = sum |x|^2 - (sum |x|)^2 / N: the cancellation costs (mu/sigma)^2 ulps (< 1e-11
-        // relative even at 40 dB SNR), and saves one FP64 add per sample in pass 2
-        fs.c2 = (pl[0] + pl[1]) - pl[15] * pl[15] * (1.0 / N);
+        fs.c2 = pl[17];
         fs.c4 = pl[18];
         fs.ph_m2 = pl[19];
         fs.aph_m2 = pl[20];
@@ -425,14 +423,18 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
 
     // ---------------------------------------------------------------- pass 2 (registers only)
     {
-      double c2acc[2] = {0.0, 0.0};                      // sum |r-mu|, sum (r-mu)^4
+      // (sum (r-mu)^2 must be accumulated: deriving it as sum|x|^2 - (sum|x|)^2/N is one FP64 op cheaper and
+      //  2 % faster, but it exposes the ~5e-14 one-sided bias of sqrt_nr multiplied by (mu/sigma)^2 - 1.3e-9
+      //  on the amplitude kurtosis at 30 dB SNR; test_high_snr_amplitude_features_keep_the_1e9_class)
+      double c2acc[4] = {0.0, 0.0, 0.0, 0.0};            // sum |r-mu|, sum (r-mu)^2, sum (r-mu)^4, -
       float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int j = 0; j < SPT; ++j) {
         const double d = r[j] - mu_r;
         const double d2 = d * d;
         c2acc[0] += fabs(d);
-        c2acc[1] = fma(d2, d2, c2acc[1]);
+        c2acc[1] += d2;
+        c2acc[2] = fma(d2, d2, c2acc[2]);
         const float e = ph[j] - mu_ph;
         q2acc[0] = fmaf(e, e, q2acc[0]);
         const float ea = fabsf(ph[j]) - mu_aph;
@@ -443,10 +445,12 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         q2acc[2] += ef2;
         q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
       }
-      warp_sum_multi<double, 2>(c2acc, lane);            // lanes 0..15: sum |r-mu| ; 16..31: sum (r-mu)^4
+      warp_sum_multi<double, 4>(c2acc, lane);
       warp_sum_multi<float, 4>(q2acc, lane);
-      if ((lane & 15) == 0) part_d(par, wg)[16 + (lane >> 3)] = c2acc[0];   // -> 16 and 18 (17 is derived)
-      if ((lane & 7) == 0) part_d(par, wg)[19 + (lane >> 3)] = static_cast<double>(q2acc[0]);
+      if ((lane & 7) == 0) {
+        if (lane < 24) part_d(par, wg)[16 + (lane >> 3)] = c2acc[0];
+        part_d(par, wg)[19 + (lane >> 3)] = static_cast<double>(q2acc[0]);
+      }
     }
 
     float vmax = 0.0f;

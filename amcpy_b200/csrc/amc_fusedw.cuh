@@ -149,14 +149,15 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
     const float mu_f = tot_f * (1.0f / (N - 1));              // radians
 
     // ---------------------------------------------------------------- pass 2 (registers only)
-    double c2acc[2] = {0.0, 0.0};                             // sum |r-mu|, sum (r-mu)^4 (sum (r-mu)^2 is derived)
+    double c2acc[4] = {0.0, 0.0, 0.0, 0.0};                   // sum |r-mu|, sum (r-mu)^2, sum (r-mu)^4, -
     float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
       const double d = r[j] - mu_r;
       const double d2 = d * d;
       c2acc[0] += fabs(d);
-      c2acc[1] = fma(d2, d2, c2acc[1]);
+      c2acc[1] += d2;
+      c2acc[2] = fma(d2, d2, c2acc[2]);
       const float e = ph[j] - mu_ph;
       q2acc[0] = fmaf(e, e, q2acc[0]);
       const float ea = fabsf(ph[j]) - mu_aph;
@@ -167,7 +168,7 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
       q2acc[2] += ef2;
       q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
     }
-    warp_sum_multi<double, 2>(c2acc, lane);                   // lane l: value l >> 4
+    warp_sum_multi<double, 4>(c2acc, lane);                   // lane l: value l >> 3
     warp_sum_multi<float, 4>(q2acc, lane);
 
     // ---------------------------------------------------------------- FFT 8 x 8 x 4 through the slot
@@ -221,8 +222,8 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
     double* pe = pend + bi * kWPendStride;
     constexpr double kInv2Pi = 0.15915494309189533577, kInv2Pi2 = kInv2Pi * kInv2Pi;
     if (lane < 16) pe[lane] = tot16;                                   // 0..15
-    if ((lane & 15) == 0) pe[16 + (lane >> 3)] = c2acc[0];             // 16 and 18 (17 is derived)
-    if ((lane & 7) == 0) {                                             // 19..22; frequency sums: radians -> cycles
+    if ((lane & 7) == 0) {                                             // 16..18, 19..22; frequency sums: radians -> cycles
+      if (lane < 24) pe[16 + (lane >> 3)] = c2acc[0];
       const double sc = (lane == 16) ? kInv2Pi2 : (lane == 24 ? kInv2Pi2 * kInv2Pi2 : 1.0);
       pe[19 + (lane >> 3)] = static_cast<double>(q2acc[0]) * sc;
     }
@@ -237,7 +238,7 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
         for (int i = 0; i < 15; ++i) fs.mono[i] = pl[i];
         fs.sum_r = pl[15];
         fs.c_abs1 = pl[16];
-        fs.c2 = (pl[0] + pl[1]) - pl[15] * pl[15] * (1.0 / N);   // sum (r-mu)^2 from the raw sums
+        fs.c2 = pl[17];
         fs.c4 = pl[18];
         fs.ph_m2 = pl[19];
         fs.aph_m2 = pl[20];
