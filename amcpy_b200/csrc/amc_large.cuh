@@ -35,15 +35,28 @@ struct LargeCfg {
   static constexpr int FFT_BYTES = N * 8;
   static constexpr int PHI_BYTES = N * 4;
   static constexpr int PART_BYTES = 2 * WARPS * 32 * 8;            // two parities x warps x 32 doubles
-  static constexpr int SMEM_BYTES = FFT_BYTES + PHI_BYTES + PART_BYTES + 64;
+  static constexpr int BATCH = 32;                                 // frames finalised together, one lane each
+  static constexpr int PEND_STRIDE = 25;                           // doubles per parked frame (odd: conflict-free)
+  static constexpr int PEND_BYTES = BATCH * PEND_STRIDE * 8;
+  static constexpr int SMEM_BYTES = FFT_BYTES + PHI_BYTES + PART_BYTES + PEND_BYTES + 64;
   static constexpr int R4 = N / 4096;                              // radix of the last stage
   static constexpr int BPT = (N / 16) / THREADS;                   // radix-16 butterflies per thread: 2
 };
 
-template <typename CT>
-__device__ __forceinline__ void load_global_sample(const CT* __restrict__ p, double& a, double& b, float& af, float& bf) {
-  load_sample<CT>(p, a, b, af, bf);
+// value already in registers -> (a, b) in FP64 and FP32
+__device__ __forceinline__ void split_sample(double2 v, double& a, double& b, float& af, float& bf) {
+  a = v.x;
+  b = v.y;
+  af = static_cast<float>(a);
+  bf = static_cast<float>(b);
 }
+__device__ __forceinline__ void split_sample(float2 v, double& a, double& b, float& af, float& bf) {
+  af = v.x;
+  bf = v.y;
+  a = static_cast<double>(af);
+  b = static_cast<double>(bf);
+}
+constexpr int kLargeU = 4;   // samples per thread per software-pipelined group (loads of group g+1 fly during group g)
 
 // one in-place radix-16 Stockham stage over the whole frame (BPT butterflies per thread)
 template <int N, int NS, int BPT, int THREADS>
@@ -82,6 +95,8 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
   float2* buf = reinterpret_cast<float2*>(smem_raw);
   float* phi = reinterpret_cast<float*>(smem_raw + Cfg::FFT_BYTES);
   double* part = reinterpret_cast<double*>(smem_raw + Cfg::FFT_BYTES + Cfg::PHI_BYTES);
+  double* pend = reinterpret_cast<double*>(smem_raw + Cfg::FFT_BYTES + Cfg::PHI_BYTES + Cfg::PART_BYTES);
+  const int my_frames = blockIdx.x < n_frames ? static_cast<int>((n_frames - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr unsigned FULL = 0xffffffffu;
 
@@ -96,18 +111,36 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     mono.clear();
     double sum_r = 0.0;
     float s_ph = 0.0f, s_aph = 0.0f;
-#pragma unroll 4
-    for (int i = tid; i < N; i += THREADS) {
-      double a, b;
-      float af, bf;
-      load_global_sample<CT>(x + i, a, b, af, bf);
-      const double s = mono.add(a, b);
-      sum_r += sqrt_nr(s);
-      const float p = atan2_fast(bf, af);
-      buf[swz16(i)] = make_float2(af, bf);
-      phi[i] = p;
-      s_ph += p;
-      s_aph += fabsf(p);
+    // software-pipelined: the 16-byte loads of the next group are issued before the current group is
+    // processed (ncu: 32 % of the stall samples were long-scoreboard waits on these loads)
+    {
+      CT nx[kLargeU];
+#pragma unroll
+      for (int u = 0; u < kLargeU; ++u) nx[u] = x[tid + THREADS * u];
+#pragma unroll 1
+      for (int i0 = tid; i0 < N; i0 += THREADS * kLargeU) {
+        CT cur[kLargeU];
+#pragma unroll
+        for (int u = 0; u < kLargeU; ++u) cur[u] = nx[u];
+        if (i0 + THREADS * kLargeU < N) {
+#pragma unroll
+          for (int u = 0; u < kLargeU; ++u) nx[u] = x[i0 + THREADS * (kLargeU + u)];
+        }
+#pragma unroll
+        for (int u = 0; u < kLargeU; ++u) {
+          const int i = i0 + THREADS * u;
+          double a, b;
+          float af, bf;
+          split_sample(cur[u], a, b, af, bf);
+          const double s = mono.add(a, b);
+          sum_r += sqrt_nr(s);
+          const float p = atan2_fast(bf, af);
+          buf[swz16(i)] = make_float2(af, bf);
+          phi[i] = p;
+          s_ph += p;
+          s_aph += fabsf(p);
+        }
+      }
     }
     __syncthreads();
     // ---------------------------------------------------------------- pass 1b: sum of wrapped differences
@@ -152,11 +185,22 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     // ---------------------------------------------------------------- pass 2: centred sums
     double c2acc[4] = {0.0, 0.0, 0.0, 0.0};
     float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 4
-    for (int i = tid; i < N; i += THREADS) {
-      double a, b;
-      float af, bf;
-      load_global_sample<CT>(x + i, a, b, af, bf);
+    CT nx2[kLargeU];                                           // same software pipeline (L2-resident re-read)
+#pragma unroll
+    for (int u = 0; u < kLargeU; ++u) nx2[u] = x[tid + THREADS * u];
+#pragma unroll 1
+    for (int i0 = tid; i0 < N; i0 += THREADS * kLargeU) {
+      CT cur[kLargeU];
+#pragma unroll
+      for (int u = 0; u < kLargeU; ++u) cur[u] = nx2[u];
+      if (i0 + THREADS * kLargeU < N) {
+#pragma unroll
+        for (int u = 0; u < kLargeU; ++u) nx2[u] = x[i0 + THREADS * (kLargeU + u)];
+      }
+#pragma unroll
+      for (int u = 0; u < kLargeU; ++u) {
+      const int i = i0 + THREADS * u;
+      const double a = static_cast<double>(cur[u].x), b = static_cast<double>(cur[u].y);
       const double d = sqrt_nr(fma(a, a, b * b)) - mu_r;
       const double d2 = d * d;
       c2acc[0] += fabs(d);
@@ -181,6 +225,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
         const float ef2 = ef * ef;
         q2acc[2] += ef2;
         q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
+      }
       }
     }
     warp_sum_multi<double, 4>(c2acc, lane);
@@ -219,28 +264,46 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     __syncthreads();                                                     // totals complete; buf/phi free again
 
     if (warp == 0) {                                                     // other warps start the next frame
-      double v = 0.0;
-      if (lane < 28) {
+      // park this frame's 25 totals (lane i sums value i over the warps); every BATCH frames the warp
+      // finalises BATCH frames at once, one lane per frame - a single lane finalising every frame kept the
+      // other 15 warps waiting at the next frame's first barrier for 17 % of their time (latency-bound FP64 chain)
+      const int bi = it % Cfg::BATCH;
+      double* pe = pend + bi * Cfg::PEND_STRIDE;
+      // slot of value i in the per-warp partial rows: 0..15 | 18 (sum f) | 20,21,22 | 24..27 | 28 (max)
+      if (lane < 25) {
+        const int src = lane < 16 ? lane : (lane < 19 ? lane + 4 : (lane < 23 ? lane + 5 : (lane == 23 ? 18 : 28)));
+        double v = pall[src];
+        if (lane == 24) {
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) v += pall[w * 32 + lane];
-      } else if (lane == 28) {
+          for (int w = 1; w < WARPS; ++w) v = fmax(v, pall[w * 32 + src]);
+        } else {
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) v = fmax(v, pall[w * 32 + 28]);
+          for (int w = 1; w < WARPS; ++w) v += pall[w * 32 + src];
+        }
+        pe[lane] = v;
       }
-      FrameSums fs;
+      if (bi == Cfg::BATCH - 1 || it == my_frames - 1) {
+        __syncwarp();
+        if (lane <= bi) {
+          const double* pl = pend + lane * Cfg::PEND_STRIDE;
+          FrameSums fs;
 #pragma unroll
-      for (int i = 0; i < 15; ++i) fs.mono[i] = __shfl_sync(FULL, v, i);
-      fs.sum_r = __shfl_sync(FULL, v, 15);
-      fs.mean_f = __shfl_sync(FULL, v, 18) / (N - 1);
-      fs.c_abs1 = __shfl_sync(FULL, v, 20);
-      fs.c2 = __shfl_sync(FULL, v, 21);
-      fs.c4 = __shfl_sync(FULL, v, 22);
-      fs.ph_m2 = __shfl_sync(FULL, v, 24);
-      fs.aph_m2 = __shfl_sync(FULL, v, 25);
-      fs.f_m2 = __shfl_sync(FULL, v, 26);
-      fs.f_m4 = __shfl_sync(FULL, v, 27);
-      fs.spec_max = __shfl_sync(FULL, v, 28);
-      if (lane == 0) finalize_features(fs, N, out + f * out_stride);
+          for (int i = 0; i < 15; ++i) fs.mono[i] = pl[i];
+          fs.sum_r = pl[15];
+          fs.c_abs1 = pl[16];
+          fs.c2 = pl[17];
+          fs.c4 = pl[18];
+          fs.ph_m2 = pl[19];
+          fs.aph_m2 = pl[20];
+          fs.f_m2 = pl[21];
+          fs.f_m4 = pl[22];
+          fs.mean_f = pl[23] / (N - 1);
+          fs.spec_max = pl[24];
+          const int64_t fo = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it - bi + lane) * gridDim.x;
+          finalize_features(fs, N, out + fo * out_stride);
+        }
+        __syncwarp();
+      }
     }
   }
 }
