@@ -58,17 +58,27 @@ __device__ __forceinline__ void split_sample(float2 v, double& a, double& b, flo
 }
 constexpr int kLargeU = 4;   // samples per thread per software-pipelined group (loads of group g+1 fly during group g)
 
-// one in-place radix-16 Stockham stage over the whole frame (BPT butterflies per thread)
+// one in-place radix-16 Stockham stage over the whole frame (BPT butterflies per thread).
+// swz16(e) = e ^ ((e >> 4) & 15); for the three stage shapes the swizzle term is known in closed form, so
+// every exchange address is base + immediate or one XOR of the byte address (the generic form cost
+// three integer instructions per element):
+//   reads  e = j + (N/16) q            : (e>>4)&15 = (j>>4)&15                 -> (j ^ ((j>>4)&15)) + (N/16) q
+//   writes NS = 1   e = 16 j + q       : (e>>4)&15 = j & 15                    -> 16 j + (q ^ (j & 15))
+//          NS = 16  e = 256 (j/16) + 16 q + k : (e>>4)&15 = q                  -> 256 (j/16) + 16 q + (k ^ q)
+//          NS = 256 e = 4096 (j/256) + 256 q + k : (e>>4)&15 = (k>>4)&15       -> ... + 256 q + (k ^ ((k>>4)&15))
 template <int N, int NS, int BPT, int THREADS>
 __device__ __forceinline__ void large_stage16(float2* __restrict__ buf, const float2* __restrict__ tw, int tid) {
+  static_assert((N / 256) % 16 == 0, "closed-form swizzle needs (N/16)/16 to be a multiple of 16");
   float2 v[BPT][16];
 #pragma unroll
   for (int bb = 0; bb < BPT; ++bb) {
     const int j = tid + THREADS * bb;
+    const float2* src = buf + (j ^ ((j >> 4) & 15));
 #pragma unroll
-    for (int q = 0; q < 16; ++q) v[bb][q] = buf[swz16(j + (N / 16) * q)];
+    for (int q = 0; q < 16; ++q) v[bb][q] = src[(N / 16) * q];
   }
   __syncthreads();                                                 // all reads of this stage are done
+  const uint32_t buf_s = smem_u32(buf);                            // 128-byte aligned
 #pragma unroll
   for (int bb = 0; bb < BPT; ++bb) {
     const int j = tid + THREADS * bb;
@@ -78,9 +88,27 @@ __device__ __forceinline__ void large_stage16(float2* __restrict__ buf, const fl
       for (int q = 1; q < 16; ++q) v[bb][q] = c_mul(v[bb][q], tw[(q - 1) * NS + k]);
     }
     dft16(v[bb]);
-    const int base = (j / NS) * NS * 16 + k;
+    if constexpr (NS == 1) {
+      const uint32_t a0 = (buf_s + 128u * j) ^ (8u * (j & 15));
 #pragma unroll
-    for (int q = 0; q < 16; ++q) buf[swz16(base + NS * q)] = v[bb][bitrev4(q)];
+      for (int q = 0; q < 16; ++q) {
+        const float2 o = v[bb][bitrev4(q)];
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a0 ^ (8u * q)), "f"(o.x), "f"(o.y) : "memory");
+      }
+    } else if constexpr (NS == 16) {
+      const uint32_t a0 = buf_s + 2048u * (j >> 4) + 8u * k;         // bits 3..6 hold k
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float2 o = v[bb][bitrev4(q)];
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((a0 ^ (8u * q)) + 128u * q), "f"(o.x), "f"(o.y)
+                     : "memory");
+      }
+    } else {
+      static_assert(NS == 256, "stage shapes: 1, 16, 256");
+      float2* dst = buf + (j >> 8) * 4096 + (k ^ ((k >> 4) & 15));
+#pragma unroll
+      for (int q = 0; q < 16; ++q) dst[256 * q] = v[bb][bitrev4(q)];
+    }
   }
   __syncthreads();
 }
@@ -111,27 +139,21 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     mono.clear();
     double sum_r = 0.0;
     float s_ph = 0.0f, s_aph = 0.0f;
-    // software-pipelined: the 16-byte loads of the next group are issued before the current group is
-    // processed (ncu: 32 % of the stall samples were long-scoreboard waits on these loads)
+    // software-pipelined with two register buffers (ping-pong, no loop-carried moves): the 16-byte loads of
+    // the next group are issued before the current group is processed (ncu: 32 % of the stall samples
+    // were long-scoreboard waits on these loads)
     {
-      CT nx[kLargeU];
+      auto load_group = [&](CT (&g)[kLargeU], int i0) {
 #pragma unroll
-      for (int u = 0; u < kLargeU; ++u) nx[u] = x[tid + THREADS * u];
-#pragma unroll 1
-      for (int i0 = tid; i0 < N; i0 += THREADS * kLargeU) {
-        CT cur[kLargeU];
-#pragma unroll
-        for (int u = 0; u < kLargeU; ++u) cur[u] = nx[u];
-        if (i0 + THREADS * kLargeU < N) {
-#pragma unroll
-          for (int u = 0; u < kLargeU; ++u) nx[u] = x[i0 + THREADS * (kLargeU + u)];
-        }
+        for (int u = 0; u < kLargeU; ++u) g[u] = x[i0 + THREADS * u];
+      };
+      auto pass1_group = [&](const CT (&g)[kLargeU], int i0) {
 #pragma unroll
         for (int u = 0; u < kLargeU; ++u) {
           const int i = i0 + THREADS * u;
           double a, b;
           float af, bf;
-          split_sample(cur[u], a, b, af, bf);
+          split_sample(g[u], a, b, af, bf);
           const double s = mono.add(a, b);
           sum_r += sqrt_nr(s);
           const float p = atan2_fast(bf, af);
@@ -140,6 +162,17 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
           s_ph += p;
           s_aph += fabsf(p);
         }
+      };
+      constexpr int STEP = THREADS * kLargeU;               // samples per group over the whole CTA
+      static_assert(N % (2 * STEP) == 0, "ping-pong loop needs an even number of groups");
+      CT ga[kLargeU], gb[kLargeU];
+      load_group(ga, tid);
+#pragma unroll 1
+      for (int i0 = tid; i0 < N; i0 += 2 * STEP) {
+        load_group(gb, i0 + STEP);
+        pass1_group(ga, i0);
+        if (i0 + 2 * STEP < N) load_group(ga, i0 + 2 * STEP);
+        pass1_group(gb, i0 + STEP);
       }
     }
     __syncthreads();
@@ -185,47 +218,52 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     // ---------------------------------------------------------------- pass 2: centred sums
     double c2acc[4] = {0.0, 0.0, 0.0, 0.0};
     float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    CT nx2[kLargeU];                                           // same software pipeline (L2-resident re-read)
+    {                                                          // same software pipeline (L2-resident re-read)
+      auto load_group = [&](CT (&g)[kLargeU], int i0) {
 #pragma unroll
-    for (int u = 0; u < kLargeU; ++u) nx2[u] = x[tid + THREADS * u];
-#pragma unroll 1
-    for (int i0 = tid; i0 < N; i0 += THREADS * kLargeU) {
-      CT cur[kLargeU];
+        for (int u = 0; u < kLargeU; ++u) g[u] = x[i0 + THREADS * u];
+      };
+      auto pass2_group = [&](const CT (&g)[kLargeU], int i0) {
 #pragma unroll
-      for (int u = 0; u < kLargeU; ++u) cur[u] = nx2[u];
-      if (i0 + THREADS * kLargeU < N) {
-#pragma unroll
-        for (int u = 0; u < kLargeU; ++u) nx2[u] = x[i0 + THREADS * (kLargeU + u)];
-      }
-#pragma unroll
-      for (int u = 0; u < kLargeU; ++u) {
-      const int i = i0 + THREADS * u;
-      const double a = static_cast<double>(cur[u].x), b = static_cast<double>(cur[u].y);
-      const double d = sqrt_nr(fma(a, a, b * b)) - mu_r;
-      const double d2 = d * d;
-      c2acc[0] += fabs(d);
-      c2acc[1] += d2;
-      c2acc[2] = fma(d2, d2, c2acc[2]);
-      const float p = phi[i];
-      const float e = p - mu_ph;
-      q2acc[0] = fmaf(e, e, q2acc[0]);
-      const float ea = fabsf(p) - mu_aph;
-      q2acc[1] = fmaf(ea, ea, q2acc[1]);
-      if (i < N - 1) {
-        float dd = phi[i + 1] - p;
-        const float over = fabsf(dd) - kPiF;
-        float fj;
-        if (fabsf(over) < kTieEps) {
-          fj = exact_freq_step<CT>(x, i);
-        } else {
-          if (over > 0.0f) dd -= copysignf(kTwoPiF, dd);
-          fj = dd * kInvTwoPiF;
+        for (int u = 0; u < kLargeU; ++u) {
+          const int i = i0 + THREADS * u;
+          const double a = static_cast<double>(g[u].x), b = static_cast<double>(g[u].y);
+          const double d = sqrt_nr(fma(a, a, b * b)) - mu_r;
+          const double d2 = d * d;
+          c2acc[0] += fabs(d);
+          c2acc[1] += d2;
+          c2acc[2] = fma(d2, d2, c2acc[2]);
+          const float p = phi[i];
+          const float e = p - mu_ph;
+          q2acc[0] = fmaf(e, e, q2acc[0]);
+          const float ea = fabsf(p) - mu_aph;
+          q2acc[1] = fmaf(ea, ea, q2acc[1]);
+          if (i < N - 1) {
+            float dd = phi[i + 1] - p;
+            const float over = fabsf(dd) - kPiF;
+            float fj;
+            if (fabsf(over) < kTieEps) {
+              fj = exact_freq_step<CT>(x, i);
+            } else {
+              if (over > 0.0f) dd -= copysignf(kTwoPiF, dd);
+              fj = dd * kInvTwoPiF;
+            }
+            const float ef = fj - mu_f;
+            const float ef2 = ef * ef;
+            q2acc[2] += ef2;
+            q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
+          }
         }
-        const float ef = fj - mu_f;
-        const float ef2 = ef * ef;
-        q2acc[2] += ef2;
-        q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
-      }
+      };
+      constexpr int STEP = THREADS * kLargeU;
+      CT ga[kLargeU], gb[kLargeU];
+      load_group(ga, tid);
+#pragma unroll 1
+      for (int i0 = tid; i0 < N; i0 += 2 * STEP) {
+        load_group(gb, i0 + STEP);
+        pass2_group(ga, i0);
+        if (i0 + 2 * STEP < N) load_group(ga, i0 + 2 * STEP);
+        pass2_group(gb, i0 + STEP);
       }
     }
     warp_sum_multi<double, 4>(c2acc, lane);
@@ -247,7 +285,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
         const int j = tid + THREADS * bb;
         float2 u[R4];
 #pragma unroll
-        for (int q = 0; q < R4; ++q) u[q] = buf[swz16(j + 4096 * q)];
+        for (int q = 0; q < R4; ++q) u[q] = buf[(j ^ ((j >> 4) & 15)) + 4096 * q];   // = swz16(j + 4096 q)
 #pragma unroll
         for (int q = 1; q < R4; ++q) u[q] = c_mul(u[q], g_tw_l4[tw_l4_offset(N) + (q - 1) * 4096 + j]);
         if constexpr (R4 == 2) {
