@@ -77,6 +77,12 @@ __device__ __forceinline__ void large_stage16(float2* __restrict__ buf, const fl
 #pragma unroll
     for (int q = 0; q < 16; ++q) v[bb][q] = src[(N / 16) * q];
   }
+  // the first butterfly's twiddles are fetched BEFORE the barrier (L2 latency hides behind it)
+  float2 tw0[15];
+  if constexpr (NS > 1) {
+#pragma unroll
+    for (int q = 1; q < 16; ++q) tw0[q - 1] = tw[(q - 1) * NS + (tid % NS)];
+  }
   __syncthreads();                                                 // all reads of this stage are done
   const uint32_t buf_s = smem_u32(buf);                            // 128-byte aligned
 #pragma unroll
@@ -85,7 +91,7 @@ __device__ __forceinline__ void large_stage16(float2* __restrict__ buf, const fl
     const int k = j % NS;
     if constexpr (NS > 1) {
 #pragma unroll
-      for (int q = 1; q < 16; ++q) v[bb][q] = c_mul(v[bb][q], tw[(q - 1) * NS + k]);
+      for (int q = 1; q < 16; ++q) v[bb][q] = c_mul(v[bb][q], bb == 0 ? tw0[q - 1] : tw[(q - 1) * NS + k]);
     }
     dft16(v[bb]);
     if constexpr (NS == 1) {
@@ -147,6 +153,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
 #pragma unroll
         for (int u = 0; u < kLargeU; ++u) g[u] = x[i0 + THREADS * u];
       };
+      float2* buf_t = buf + (tid ^ ((tid >> 4) & 15));      // swizzled position of sample tid (+ multiples of THREADS)
       auto pass1_group = [&](const CT (&g)[kLargeU], int i0) {
 #pragma unroll
         for (int u = 0; u < kLargeU; ++u) {
@@ -157,7 +164,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
           const double s = mono.add(a, b);
           sum_r += sqrt_nr(s);
           const float p = atan2_fast(bf, af);
-          buf[swz16(i)] = make_float2(af, bf);
+          buf_t[i - tid] = make_float2(af, bf);           // = buf[swz16(i)]: (i >> 4) & 15 == (tid >> 4) & 15
           phi[i] = p;
           s_ph += p;
           s_aph += fabsf(p);
@@ -165,6 +172,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
       };
       constexpr int STEP = THREADS * kLargeU;               // samples per group over the whole CTA
       static_assert(N % (2 * STEP) == 0, "ping-pong loop needs an even number of groups");
+      static_assert(THREADS % 256 == 0, "closed-form swizzle of the FP32 copy needs THREADS/16 to be a multiple of 16");
       CT ga[kLargeU], gb[kLargeU];
       load_group(ga, tid);
 #pragma unroll 1
