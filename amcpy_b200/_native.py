@@ -86,6 +86,7 @@ SIGNATURES = {
     "amc_launch_count": (_I64, []),
     "amc_extract_batch": (_INT, [_P, _INT, _I64, _I64, _I64, _I64, _P, _I64, _U32, _INT, _P]),
     "amc_extract_host": (_INT, [_P, _INT, _I64, _I64, _I64, _I64, _P, _I64, _U32, _INT, _INT]),
+    "amc_extract_host_planar": (_INT, [_P, _P, _INT, _I64, _I64, _I64, _P, _I64, _U32, _INT, _INT]),
     "amc_frames_from_sample_major": (_INT, [_P, _INT, _I64, _I64, _I64, _P, _P]),
     "amc_instantaneous_batch": (_INT, [_P, _INT, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "amc_moments_batch": (_INT, [_P, _INT, _I64, _I64, _I64, _I64, _P, _P]),

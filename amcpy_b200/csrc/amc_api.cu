@@ -508,4 +508,86 @@ int amc_extract_host(const void* iq, int iq_dtype, int64_t n_frames, int64_t fra
   return status;
 }
 
+int amc_extract_host_planar(const void* re, const void* im, int iq_dtype, int64_t n_frames, int64_t frame_size,
+                            int64_t sample_stride, double* out, int64_t out_stride, uint32_t feature_mask, int flags,
+                            int device) {
+  int rc = check_common(re, iq_dtype, n_frames, frame_size, 1, sample_stride);
+  if (rc != AMC_OK) return rc;
+  if ((feature_mask & AMC_ALL_FEATURES) == 0) return fail(AMC_ERR_INVALID_ARG, "feature_mask selects nothing");
+  if (out_stride < AMC_N_FEATURES) return fail(AMC_ERR_INVALID_ARG, "out_stride %lld < 18", (long long)out_stride);
+  if (n_frames == 0) return AMC_OK;
+  if (out == nullptr) return fail(AMC_ERR_INVALID_ARG, "out is NULL");
+  if (sample_stride < n_frames) return fail(AMC_ERR_INVALID_ARG, "sample_stride < n_frames");
+  if (frame_size > 65535LL * 32) return fail(AMC_ERR_UNSUPPORTED, "frame_size too large for the re-layout grid");
+  if (device < 0 || device >= kMaxDevices) return fail(AMC_ERR_INVALID_ARG, "device %d out of range", device);
+  int prev = 0;
+  AMC_CUDA(cudaGetDevice(&prev));
+  AMC_CUDA(cudaSetDevice(device));
+
+  const size_t relt = iq_dtype == AMC_C128 ? 8 : 4;            // bytes per real plane element
+  const size_t frame_bytes = static_cast<size_t>(frame_size) * 2 * relt;
+  int64_t chunk = static_cast<int64_t>((64u << 20) / frame_bytes);   // ~64 MiB of samples per chunk
+  chunk = chunk < 32 ? 32 : (chunk / 32) * 32;
+  if (chunk > n_frames) chunk = n_frames;
+
+  std::lock_guard<std::mutex> lk(g_pipe_mu[device]);
+  HostPipe& p = g_pipe[device];
+  rc = ensure_pipe(p, static_cast<size_t>(chunk) * frame_bytes, static_cast<size_t>(chunk) * frame_bytes,
+                   static_cast<size_t>(chunk) * AMC_N_FEATURES * sizeof(double));
+  if (rc != AMC_OK) {
+    cudaSetDevice(prev);
+    return rc;
+  }
+  const unsigned char* src_re = static_cast<const unsigned char*>(re);
+  const unsigned char* src_im = static_cast<const unsigned char*>(im);
+  int status = AMC_OK;
+  int64_t c = 0;
+  for (int64_t f0 = 0; f0 < n_frames && status == AMC_OK; f0 += chunk, ++c) {
+    const int b = static_cast<int>(c & 1);
+    const int64_t nf = (n_frames - f0) < chunk ? (n_frames - f0) : chunk;
+    cudaStream_t st = p.stream[b];
+    unsigned char* d_re = static_cast<unsigned char*>(p.d_in[b]);
+    unsigned char* d_im = d_re + static_cast<size_t>(nf) * frame_size * relt;   // second half of the staging buffer
+    const size_t row = static_cast<size_t>(nf) * relt, pitch = static_cast<size_t>(sample_stride) * relt;
+    cudaError_t e = cudaMemcpy2DAsync(d_re, row, src_re + static_cast<size_t>(f0) * relt, pitch, row,
+                                      static_cast<size_t>(frame_size), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && src_im)
+      e = cudaMemcpy2DAsync(d_im, row, src_im + static_cast<size_t>(f0) * relt, pitch, row,
+                            static_cast<size_t>(frame_size), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) {
+      status = fail(AMC_ERR_CUDA, "host->device copy failed: %s", cudaGetErrorString(e));
+      break;
+    }
+    dim3 grid(static_cast<unsigned>((nf + 31) / 32), static_cast<unsigned>((frame_size + 31) / 32));
+    if (iq_dtype == AMC_C128)
+      amc::frames_from_planar_kernel<double, double2><<<grid, 256, 0, st>>>(
+          reinterpret_cast<const double*>(d_re), src_im ? reinterpret_cast<const double*>(d_im) : nullptr, nf,
+          static_cast<int>(frame_size), nf, static_cast<double2*>(p.d_tr[b]));
+    else
+      amc::frames_from_planar_kernel<float, float2><<<grid, 256, 0, st>>>(
+          reinterpret_cast<const float*>(d_re), src_im ? reinterpret_cast<const float*>(d_im) : nullptr, nf,
+          static_cast<int>(frame_size), nf, static_cast<float2*>(p.d_tr[b]));
+    ++t_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      status = fail(AMC_ERR_CUDA, "re-layout launch failed: %s", cudaGetErrorString(e));
+      break;
+    }
+    status = amc_extract_batch(p.d_tr[b], iq_dtype, nf, frame_size, frame_size, 1, p.d_out[b], AMC_N_FEATURES,
+                               feature_mask, flags, st);
+    if (status != AMC_OK) break;
+    e = cudaMemcpy2DAsync(out + f0 * out_stride, static_cast<size_t>(out_stride) * sizeof(double), p.d_out[b],
+                          AMC_N_FEATURES * sizeof(double), AMC_N_FEATURES * sizeof(double), static_cast<size_t>(nf),
+                          cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) status = fail(AMC_ERR_CUDA, "device->host copy failed: %s", cudaGetErrorString(e));
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaStreamSynchronize(p.stream[i]);
+    if (e != cudaSuccess && status == AMC_OK)
+      status = fail(AMC_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
+  }
+  cudaSetDevice(prev);
+  return status;
+}
+
 }  // extern "C"

@@ -333,4 +333,36 @@ frames_from_sample_major_kernel(const CT* __restrict__ src, int64_t n_frames, in
   }
 }
 
+// Planar (split real / imaginary planes, as stored in a Level-5 .mat file) and sample-major:
+// plane element (f, n) at f + n*src_sample_stride; dst (f, n) at f*N + n, interleaved complex.
+// `im` may be NULL (real input).  32x32 tiles through smem.
+template <typename RT, typename CT>
+__global__ void __launch_bounds__(256)
+frames_from_planar_kernel(const RT* __restrict__ re, const RT* __restrict__ im, int64_t n_frames, int n,
+                          int64_t src_sample_stride, CT* __restrict__ dst) {
+  __shared__ CT tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int64_t f0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int n0 = blockIdx.y * 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int nn = n0 + ty + 8 * k;
+    const int64_t ff = f0 + tx;
+    if (nn < n && ff < n_frames) {
+      const int64_t o = static_cast<int64_t>(nn) * src_sample_stride + ff;
+      CT v;
+      v.x = re[o];
+      v.y = im ? im[o] : static_cast<RT>(0);
+      tile[ty + 8 * k][tx] = v;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t ff = f0 + ty + 8 * k;
+    const int nn = n0 + tx;
+    if (nn < n && ff < n_frames) dst[ff * n + nn] = tile[tx][ty + 8 * k];
+  }
+}
+
 }  // namespace amc

@@ -10,6 +10,9 @@ What replaces the 6 processes x num_threads threads x Queue: the file is parsed 
 modulation's Fortran-ordered block goes to a GPU in place (sample-major, no host transpose) through
 the library's chunked copy/compute pipeline, and the modulations are spread over the visible GPUs
 (one host thread per GPU; under torchrun one rank per GPU takes every world_size-th modulation).
+An uncompressed Level-5 file (scipy's `savemat` default) is not even parsed by scipy: `matio.read_planar`
+memory-maps the separately stored real / imaginary planes and the GPU interleaves them
+(`ops.extract_features_host_planar`); compressed (`save -v7`) files go through `scipy.io.loadmat`.
 Deliberate deviations from the reference: shape mismatches and per-modulation
 failures raise instead of being printed over, and elapsed (not CPU) time is reported.
 """
@@ -17,13 +20,14 @@ failures raise instead of being printed over, and elapsed (not CPU) time is repo
 from __future__ import annotations
 
 import os
+import threading
 import time
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import scipy.io
 
-from . import ops
+from . import matio, ops
 from .config import Config
 
 
@@ -68,6 +72,55 @@ def extract_modulation(parsed: np.ndarray, n_snr: int, n_frames: int, frame_size
     return fm
 
 
+def extract_modulation_planar(arr: "matio.PlanarArray", n_snr: int, n_frames: int, frame_size: int,
+                              device: int = 0) -> np.ndarray:
+    """Same result as `extract_modulation` from the memory-mapped planes of a Level-5 variable: element
+    (snr, frame, sample) of the column-major (S, F, L) variable is plane[snr + S*frame + S*F*sample], i.e.
+    frame q = snr + S*frame of a sample-major block with sample stride S*F."""
+    if len(arr.shape) != 3:
+        raise ValueError(f"expected a 3-D (snr, frame, sample) array, got shape {arr.shape}")
+    S, F, L = arr.shape
+    if S < n_snr or F < n_frames or L < frame_size:
+        raise ValueError(
+            f"data shape {arr.shape} is smaller than the configured "
+            f"(n_snr={n_snr}, num_frames={n_frames}, frame_size={frame_size})"
+        )
+    nq = S * n_frames
+    feats = ops.extract_features_host_planar(arr.re, arr.im, nq, frame_size, S * F, device=device)
+    fm = np.zeros((n_snr, n_frames, ops.N_FEATURES), dtype=np.float32)  # feature_extraction.py:56
+    idx = np.arange(nq)
+    si, fi = idx % S, idx // S
+    keep = si < n_snr
+    fm[si[keep], fi[keep], :] = feats[keep]  # float64 -> float32 on store (feature_extraction.py:35)
+    return fm
+
+
+class _MatSource:
+    """The input file, parsed once: memory-mapped planes when the file allows it, scipy.io.loadmat otherwise
+    (loaded lazily and only if some variable needs it)."""
+
+    def __init__(self, path):
+        self.path = str(path)
+        self.planar = matio.read_planar(self.path) or {}
+        self._mat = None
+        self._lock = threading.Lock()   # run_extraction uses one host thread per GPU
+
+    def loadmat(self):
+        with self._lock:
+            if self._mat is None:
+                self._mat = scipy.io.loadmat(self.path)
+            return self._mat
+
+    def features(self, key: str, modulation: str, n_snr: int, n_frames: int, frame_size: int, device: int):
+        arr = self.planar.get(key)
+        if arr is not None and len(arr.shape) == 3:
+            return extract_modulation_planar(arr, n_snr, n_frames, frame_size, device=device)
+        mat = self.loadmat()
+        if key not in mat:
+            raise KeyError(f"variable {key!r} for {modulation} not found in {self.path}")
+        return extract_modulation(mat[key], n_snr, n_frames, frame_size, device=device)
+
+
 def _rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -77,12 +130,10 @@ def _modulation_process(modulation: str, cfg: Config, data_mat=None, device: int
     t0 = time.perf_counter()
     print(f"[{modulation}] Starting feature extraction on cuda:{device} ...")
     if data_mat is None:
-        data_mat = scipy.io.loadmat(str(cfg.paths.mat_data / cfg.paths.mat_filename))
+        data_mat = _MatSource(cfg.paths.mat_data / cfg.paths.mat_filename)
     key = cfg.signals.mat_info[modulation]
-    if key not in data_mat:
-        raise KeyError(f"variable {key!r} for {modulation} not found in {cfg.paths.mat_filename}")
-    fm = extract_modulation(data_mat[key], len(cfg.signals.snr_values), cfg.signals.num_frames,
-                            cfg.signals.frame_size, device=device)
+    fm = data_mat.features(key, modulation, len(cfg.signals.snr_values), cfg.signals.num_frames,
+                           cfg.signals.frame_size, device)
     out_path = cfg.paths.calculated_features / f"{modulation}_features.mat"
     scipy.io.savemat(str(out_path), {"Modulation": modulation, key: fm})
     print(f"[{modulation}] Done in {time.perf_counter() - t0:.2f}s -> {out_path}")
@@ -98,7 +149,7 @@ def run_extraction(cfg: Config) -> None:
     cfg.paths.ensure_dirs()
     rank, world, local_rank = _rank_world()
     mods = list(cfg.signals.modulations_with_noise)
-    data_mat = scipy.io.loadmat(str(cfg.paths.mat_data / cfg.paths.mat_filename))
+    data_mat = _MatSource(cfg.paths.mat_data / cfg.paths.mat_filename)
     if world > 1:  # one rank per GPU: every world_size-th modulation
         mine = mods[rank::world]
         for m in mine:

@@ -127,6 +127,34 @@ def extract_features_host(frames: np.ndarray, device: int = 0, out: np.ndarray |
     return out
 
 
+def extract_features_host_planar(re: np.ndarray, im: np.ndarray | None, n_frames: int, frame_size: int,
+                                 sample_stride: int, device: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+    """Planar sample-major host data (amc_extract_host_planar): `re` / `im` are flat float64 or float32 planes
+    (e.g. numpy.memmap views of a .mat file, see matio.py), plane element (f, n) at f + n*sample_stride.
+    Returns float64 (n_frames, 18)."""
+    re = np.asarray(re)
+    if re.dtype not in (np.float64, np.float32) or re.ndim != 1 or not re.flags.c_contiguous:
+        raise TypeError("re must be a flat contiguous float64/float32 array")
+    if im is not None:
+        im = np.asarray(im)
+        if im.dtype != re.dtype or im.shape != re.shape or not im.flags.c_contiguous:
+            raise TypeError("im must match re")
+    need = (frame_size - 1) * sample_stride + n_frames
+    if n_frames > 0 and re.size < need:
+        raise ValueError(f"planes hold {re.size} elements, layout needs {need}")
+    if out is None:
+        out = np.empty((n_frames, N_FEATURES), dtype=np.float64)
+    elif out.dtype != np.float64 or out.shape != (n_frames, N_FEATURES) or not out.flags.c_contiguous:
+        raise ValueError("out must be C-contiguous float64 (n_frames, 18)")
+    rc = nat.lib().amc_extract_host_planar(
+        re.ctypes.data, im.ctypes.data if im is not None else None,
+        nat.AMC_C128 if re.dtype == np.float64 else nat.AMC_C64, n_frames, frame_size, sample_stride,
+        out.ctypes.data, N_FEATURES, nat.AMC_ALL_FEATURES, 0, device,
+    )
+    nat.check(rc)
+    return out
+
+
 def frames_from_sample_major(src, n_frames: int, frame_size: int, sample_stride: int, stream=None):
     """Device re-layout of a flat sample-major block (element (f, n) at f + n*sample_stride) into
     a (n_frames, frame_size) C-contiguous tensor."""

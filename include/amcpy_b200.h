@@ -99,6 +99,18 @@ int amc_extract_host(const void* iq, int iq_dtype, int64_t n_frames, int64_t fra
                      uint32_t feature_mask, int flags, int device);
 
 /*
+ * Same for PLANAR sample-major host data: separate real and imaginary planes (float64 planes for
+ * AMC_C128, float32 for AMC_C64; `im` may be NULL for real input), plane element (f, n) at
+ * f + n*sample_stride (strides in REAL elements, sample_stride >= n_frames).  This is how a MATLAB
+ * Level-5 .mat file stores the (n_snr, n_frames, n_samples) variables the reference slices
+ * (feature_extraction.py:46-48, :68): the planes of a memory-mapped file go to the GPU as they are and
+ * are interleaved + transposed there, instead of scipy.io.loadmat doing it on one host thread.
+ */
+int amc_extract_host_planar(const void* re, const void* im, int iq_dtype, int64_t n_frames, int64_t frame_size,
+                            int64_t sample_stride, double* out, int64_t out_stride, uint32_t feature_mask,
+                            int flags, int device);
+
+/*
  * Device-side re-layout: src holds n_frames frames sample-major (element (f, n) at
  * f + n*src_sample_stride); dst receives one contiguous row of frame_size samples per frame.
  */

@@ -149,6 +149,30 @@ def test_host_pipeline_row_major_and_sample_major(torch_cuda):
         np.ascontiguousarray(flat[:, :1000])), scale=1e-3)  # padded rows through the general kernel
 
 
+def test_host_pipeline_planar_planes_match_interleaved(torch_cuda):
+    """amc_extract_host_planar (split real / imaginary sample-major planes, as memory-mapped from a .mat file)
+    feeds the same kernel the same frames as the interleaved host path: bitwise equal results."""
+    from amcpy_b200 import ops
+
+    x, _ = golden_frames(2048)
+    big = np.concatenate([x.reshape(-1, 2048)] * 40)        # 2880 frames: more than one 64 MiB chunk
+    want = ops.extract_features_host(big)
+    nf, n = big.shape
+    pad = 5                                                 # plane rows longer than the frames used
+    re = np.zeros((n, nf + pad))
+    im = np.zeros((n, nf + pad))
+    re[:, :nf], im[:, :nf] = big.real.T, big.imag.T
+    got = ops.extract_features_host_planar(re.reshape(-1), im.reshape(-1), nf, n, nf + pad)
+    assert np.array_equal(got, want)
+    got32 = ops.extract_features_host_planar(re.astype(np.float32).reshape(-1), im.astype(np.float32).reshape(-1), nf, n,
+                                             nf + pad)
+    assert np.array_equal(got32, ops.extract_features_host(big.astype(np.complex64)))
+    real_only = ops.extract_features_host_planar(re.reshape(-1), None, nf, n, nf + pad)
+    assert np.array_equal(real_only, ops.extract_features_host(big.real.astype(np.complex128)), equal_nan=True)
+    with pytest.raises(ValueError):
+        ops.extract_features_host_planar(re.reshape(-1)[:100], im.reshape(-1)[:100], nf, n, nf + pad)
+
+
 def test_determinism_and_grid_independence(torch_cuda):
     from amcpy_b200 import ops
 
@@ -188,6 +212,31 @@ def test_run_extraction_matches_reference_mat_files(torch_cuda, tmp_path):
         assert np.allclose(got, want, rtol=1.3e-6, atol=0), mod
         cols_1e9 = [c for c in range(18) if c + 1 not in (1, 2, 3, 5, 9)]
         assert np.allclose(got[..., cols_1e9], want[..., cols_1e9], rtol=1.2e-7, atol=0), mod
+
+
+def test_run_extraction_same_files_from_compressed_and_uncompressed_input(torch_cuda, tmp_path):
+    """Uncompressed Level-5 input goes through the memory-mapped planar path, compressed input through
+    scipy.io.loadmat: the written feature files must be identical."""
+    import scipy.io
+
+    from amcpy_b200 import matio, synth
+    from amcpy_b200.config import Config, Paths, SignalConfig
+    from amcpy_b200.feature_extraction import run_extraction
+
+    data = synth.dataset(SNRS, 3, 2048, 17)
+    outs = []
+    for name, compress in (("plain", False), ("zip", True)):
+        cfg = Config(paths=Paths(root=tmp_path / name), signals=SignalConfig(num_frames=3))
+        cfg.paths.ensure_dirs()
+        path = cfg.paths.mat_data / cfg.paths.mat_filename
+        scipy.io.savemat(str(path), {cfg.signals.mat_info[m]: data[i] for i, m in enumerate(synth.MODULATIONS)},
+                         do_compression=compress)
+        assert (matio.read_planar(path) is None) == compress
+        run_extraction(cfg)
+        outs.append({m: scipy.io.loadmat(str(cfg.paths.calculated_features / f"{m}_features.mat"))[cfg.signals.mat_info[m]]
+                     for m in cfg.signals.modulations_with_noise})
+    for m in outs[0]:
+        assert np.array_equal(outs[0][m], outs[1][m], equal_nan=True), m
 
 
 def test_run_extraction_fails_loudly_on_short_data(torch_cuda, tmp_path):

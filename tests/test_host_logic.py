@@ -136,3 +136,36 @@ def test_features_module_surface():
     with pytest.raises(KeyError):
         F.calculate_features([19], np.zeros(4, dtype=complex))   # unknown id: KeyError before any GPU work
     assert F.calculate_features([], np.zeros(4, dtype=complex)) == []
+
+
+def test_matio_planar_reader_matches_scipy_and_knows_its_limits(tmp_path):
+    """matio.read_planar returns zero-copy planes that reassemble to exactly what scipy.io.loadmat returns;
+    compressed files and non-float variables are left to scipy (I/O fallback only)."""
+    import scipy.io
+
+    from amcpy_b200 import matio
+
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((16, 5, 64)) + 1j * rng.standard_normal((16, 5, 64))
+    b = (rng.standard_normal((4, 3, 8)) + 1j * rng.standard_normal((4, 3, 8))).astype(np.complex64)
+    c = rng.standard_normal((2, 7))
+    p = tmp_path / "all_modulations.mat"
+    scipy.io.savemat(str(p), {"signal_qpsk": a, "signal_bpsk": b, "real": c, "Modulation": "QPSK", "ints": np.arange(4)})
+    got = matio.read_planar(p)
+    ref = scipy.io.loadmat(str(p))
+    assert set(got) == {"signal_qpsk", "signal_bpsk", "real"}          # char / integer variables are skipped
+    for k in got:
+        q = got[k]
+        full = q.re.reshape(q.shape, order="F")
+        if q.im is not None:
+            full = full + 1j * q.im.reshape(q.shape, order="F")
+        assert q.shape == ref[k].shape and np.array_equal(full, ref[k])
+        assert isinstance(q.re, np.memmap)                              # views of the file, not copies
+    assert got["signal_bpsk"].dtype == np.float32 and got["real"].im is None
+    # element (s, f, n) of the column-major variable = plane[s + S*f + S*F*n]
+    S, F, _ = a.shape
+    assert got["signal_qpsk"].re[3 + S * 2 + S * F * 10] == a[3, 2, 10].real
+    scipy.io.savemat(str(p), {"signal_qpsk": a}, do_compression=True)
+    assert matio.read_planar(p) is None
+    (tmp_path / "junk.mat").write_bytes(b"not a mat file")
+    assert matio.read_planar(tmp_path / "junk.mat") is None
