@@ -44,6 +44,17 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _physical_gpu_index(local_rank: int) -> int:
+    """NVML index of the GPU torch calls cuda:<local_rank> (CUDA_VISIBLE_DEVICES may renumber them)."""
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except (ValueError, IndexError):
+            pass
+    return local_rank
+
+
 # ------------------------------------------------------------------------------------------
 # clocks sampler (pynvml), runs during the timed region
 # ------------------------------------------------------------------------------------------
@@ -246,7 +257,7 @@ def run_cuda_arm(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.amc_launch_count()   # counted from here: the generator / warm-up launches are excluded
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(_physical_gpu_index(local_rank)) as clocks:
         barrier()
         t_all0.record(stream)
         for k in range(args.steps):
@@ -271,12 +282,7 @@ def run_cuda_arm(args):
             print(json.dumps({"profiling_only": True, "kernel_ms_per_launch": kernel_ms, "value": value}), flush=True)
         return 0
     # one rank per GPU: allocate (first-touch) the pinned staging buffers on the GPU's own NUMA node
-    physical = local_rank
-    if os.environ.get("CUDA_VISIBLE_DEVICES"):
-        try:
-            physical = int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])
-        except (ValueError, IndexError):
-            physical = local_rank
+    physical = _physical_gpu_index(local_rank)
     affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
     numa_cpus = nat.bind_host_thread_to_gpu(physical)
     xh = torch.empty((n_frames, FRAME), dtype=torch.complex128, pin_memory=True)
