@@ -67,6 +67,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Returns v, hidden from the optimiser when HIDE: values derived from it are recomputed where they are
+// used instead of being kept in (or spilled from) registers across the whole frame loop.
+template <bool HIDE>
+__device__ __forceinline__ int opaque_if(int v) {
+  if constexpr (HIDE) asm volatile("" : "+r"(v));
+  return v;
+}
+
 // ------------------------------------------------------------------ warp reductions
 // Sum V values (V a power of two <= 32) across the warp with ~V shuffles instead of 5*V:
 // at every step half of the values travel to the partner lane.  Afterwards lane l holds the

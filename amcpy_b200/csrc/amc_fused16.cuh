@@ -110,14 +110,6 @@ __global__ void init_twiddle16dif_kernel() {
 // conflict-free exchange layout for the 16 x 16 x R Stockham passes: low 4 bits ^= bits 4..7
 __device__ __forceinline__ int swz16(int e) { return e ^ ((e >> 4) & 15); }
 
-// Returns v, hidden from the optimiser when HIDE: values derived from it are recomputed where they are
-// used instead of being kept in (or spilled from) registers across the whole frame loop.
-template <bool HIDE>
-__device__ __forceinline__ int opaque_if(int v) {
-  if constexpr (HIDE) asm volatile("" : "+r"(v));
-  return v;
-}
-
 constexpr int kTRow = 17;         // float2 per lane row of the warp-private exchange buffer (16 + 1 pad)
 constexpr int kPend16Stride = 25; // doubles per parked frame (25 totals; odd stride: conflict-free lane-per-frame reads)
 

@@ -47,9 +47,10 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
   uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + 2 * Cfg::SLOT_BYTES + Cfg::FFTB_BYTES + Cfg::PEND_BYTES +
                                                Cfg::RED_BYTES);
 
-  const int64_t gg = static_cast<int64_t>(blockIdx.x) * Cfg::G + g;
-  const int64_t tg = static_cast<int64_t>(gridDim.x) * Cfg::G;
-  const uint64_t policy = l2_evict_first_policy();
+  // 32-bit group ids, L2 policy created at use, per-lane addresses recomputed from an opaque lane id: the loop
+  // sits at the 128-register limit of 2 CTAs x 256 threads and spilled exactly these loop invariants
+  const int gg = static_cast<int>(blockIdx.x) * Cfg::G + g;
+  const int tg = static_cast<int>(gridDim.x) * Cfg::G;
   const int my_frames = (gg < n_frames) ? static_cast<int>((n_frames - gg + tg - 1) / tg) : 0;
 
   if (lane == 0) {
@@ -63,7 +64,8 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
     for (int s = 0; s < 2; ++s)
       if (s < my_frames) {
         mbar_arrive_expect_tx(&bars[s], Cfg::SLOT_BYTES);
-        bulk_copy_g2s(gbase + s * Cfg::SLOT_BYTES, iq + (gg + s * tg) * frame_stride, Cfg::SLOT_BYTES, &bars[s], policy);
+        bulk_copy_g2s(gbase + s * Cfg::SLOT_BYTES, iq + (gg + static_cast<int64_t>(s) * tg) * frame_stride,
+                      Cfg::SLOT_BYTES, &bars[s], l2_evict_first_policy());
       }
   }
 
@@ -124,15 +126,16 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
 
     // 16 FP64 partials per lane -> lane l (and l + 16) holds the warp total of value l
     __syncwarp();                                             // the previous frame's column reads are done
+    const int lv = opaque_if<true>(lane);
 #pragma unroll
-    for (int i = 0; i < 15; ++i) red[lane * kWRow + i] = mono.s[i];
-    red[lane * kWRow + 15] = sum_r;
+    for (int i = 0; i < 15; ++i) red[lv * kWRow + i] = mono.s[i];
+    red[lv * kWRow + 15] = sum_r;
     float accf[4] = {s_ph, s_aph, s_f, 0.0f};
     warp_sum_multi<float, 4>(accf, lane);                     // lane l: total of value l >> 3
     __syncwarp();
     double tot16;
     {
-      const double* col = red + (lane >> 4) * (16 * kWRow) + (lane & 15);
+      const double* col = red + (lv >> 4) * (16 * kWRow) + (lv & 15);
       double cs[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) cs[i] = col[i * kWRow];
@@ -177,26 +180,29 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
     float2* buf_b = Cfg::C128 ? reinterpret_cast<float2*>(slot_ptr + N * 8) : fft_b_extra;
     float vmax = 0.0f;
     {
+      // (the ~30 swizzled exchange indices are recomputed per frame from an opaque lane id: hoisted out of the
+      // loop they were spilled and reloaded with LDL in front of every use)
+      const int lf = opaque_if<true>(lane);
       float2 v[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = make_float2(xr[q], xi[q]);
       dft8(v);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) buf_a[swz(8 * lane + q)] = v[out8(q)];
+      for (int q = 0; q < 8; ++q) buf_a[swz(8 * lf + q)] = v[out8(q)];
       __syncwarp();
-      const int k = lane & 7;
+      const int k = lf & 7;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = buf_a[swz(lane + 32 * q)];
+      for (int q = 0; q < 8; ++q) v[q] = buf_a[swz(lf + 32 * q)];
 #pragma unroll
       for (int q = 1; q < 8; ++q) v[q] = c_mul(v[q], g_tw8_s2[(q - 1) * 8 + k]);
       dft8(v);
-      const int base = (lane >> 3) * 64 + k;
+      const int base = (lf >> 3) * 64 + k;
 #pragma unroll
       for (int q = 0; q < 8; ++q) buf_b[swz(base + 8 * q)] = v[out8(q)];
       __syncwarp();
 #pragma unroll
       for (int bb = 0; bb < 2; ++bb) {
-        const int jj = lane + 32 * bb;                        // 0..63
+        const int jj = lf + 32 * bb;                          // 0..63
         float2 u[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) u[q] = buf_b[swz(jj + 64 * q)];
@@ -214,7 +220,7 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
       fence_proxy_async_smem();
       mbar_arrive_expect_tx(&bars[slot], Cfg::SLOT_BYTES);
       bulk_copy_g2s(slot_ptr, iq + (gg + static_cast<int64_t>(it + 2) * tg) * frame_stride, Cfg::SLOT_BYTES,
-                    &bars[slot], policy);
+                    &bars[slot], l2_evict_first_policy());
     }
 
     // ---------------------------------------------------------------- park this frame's 25 totals
