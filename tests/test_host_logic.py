@@ -3,6 +3,7 @@ config parity with the reference's field names/defaults, layout planning of the 
 synthetic generator, and that no product module routes through the oracle."""
 
 import ast
+import ctypes
 import re
 from pathlib import Path
 
@@ -59,6 +60,14 @@ def test_argument_checks_run_without_a_gpu(built_lib):
     assert built_lib.amc_extract_batch(None, nat.AMC_C128, 0, 16, 16, 1, None, 18, nat.AMC_ALL_FEATURES, 0, None) == 0
     assert built_lib.amc_extract_batch(None, nat.AMC_C128, 1, 16, 16, 1, None, 18, nat.AMC_ALL_FEATURES, 0, None) == -1
     assert built_lib.amc_extract_host(None, nat.AMC_C128, -1, 16, 16, 1, None, 18, nat.AMC_ALL_FEATURES, 0, 0) == -1
+    # planar entry: sample_stride must cover the frames, mask must select something, n_frames == 0 is a no-op
+    buf = (ctypes.c_double * 64)()
+    out = (ctypes.c_double * 36)()
+    assert built_lib.amc_extract_host_planar(buf, buf, nat.AMC_C128, 2, 16, 1, out, 18, nat.AMC_ALL_FEATURES, 0, 0) == -1
+    assert b"sample_stride" in built_lib.amc_last_error_string()
+    assert built_lib.amc_extract_host_planar(buf, buf, nat.AMC_C128, 2, 16, 2, out, 18, 0, 0, 0) == -1
+    assert built_lib.amc_extract_host_planar(buf, None, nat.AMC_C128, 0, 16, 2, out, 18, nat.AMC_ALL_FEATURES, 0, 0) == 0
+    assert built_lib.amc_extract_host_planar(None, None, nat.AMC_C128, 2, 16, 2, out, 18, nat.AMC_ALL_FEATURES, 0, 0) == -1
 
 
 def test_product_never_imports_the_oracle():
