@@ -13,7 +13,7 @@
 //   * the edge phase (first sample after each warp's run of 32) travels through 64 bytes of shared
 //     memory instead of one shuffle per sample;
 //   * the 18-feature finalisation is batched: warp 0 parks each frame's 25 totals in shared memory
-//     and finalises 16 frames at once, one lane per frame, instead of 32 redundant lanes per frame;
+//     and finalises 32 frames at once, one lane per frame, instead of 32 redundant lanes per frame;
 //   * only ONE block barrier per frame: stage A is written before the pass-1 barrier, the x slot is
 //     refilled by TMA right after that barrier, everything after it is warp-local, and a frame's
 //     totals are collected one frame later (double-buffered partials).
@@ -48,8 +48,9 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
   dft4(v[12], v[13], v[14], v[15]);
 }
 
-// Twiddle tables laid out the way the warps read them (lane-contiguous), so every twiddle load
-// touches one or two 128-byte lines.  (Indexing the generic W_4096 table made each load touch
+// Twiddle tables of the in-place 16 x 16 x 16 Stockham stages (now used by the long-frame kernel,
+// amc_large.cuh: rows N = 4096 of g_tw_s3), laid out the way the warps read them (lane-contiguous), so
+// every twiddle load touches one or two 128-byte lines.  (Indexing the generic W_4096 table made each load touch
 // 16-28 lines and the L1TEX pipe - not HBM, not the FP pipes - became the kernel's bottleneck:
 // 32 % of the run time, see profiles/r1_experiments.txt.)
 //   g_tw_s2[q-1][tx]        = W_256^(tx q)          q = 1..15, tx = 0..15
