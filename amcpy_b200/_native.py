@@ -22,6 +22,7 @@ HEADER = PKG.parent / "include" / "amcpy_b200.h"
 AMC_C64, AMC_C128 = 0, 1
 AMC_FLAG_FORCE_GENERAL = 1
 AMC_FLAG_FUSED_SPT8 = 2
+AMC_FLAG_FUSED_WS = 4
 AMC_ALL_FEATURES = 0x3FFFF
 
 NVCC_FLAGS = [

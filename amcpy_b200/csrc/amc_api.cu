@@ -10,6 +10,7 @@
 #include "amc_fused.cuh"
 #include "amc_fused16.cuh"
 #include "amc_fusedw.cuh"
+#include "amc_fusedws.cuh"
 #include "amc_large.cuh"
 #include "amc_general.cuh"
 #include "amc_generate.cuh"
@@ -128,6 +129,30 @@ int launch_fused16(const void* iq, int64_t n_frames, int64_t frame_stride, doubl
 }
 
 template <int N, typename CT>
+int launch_fusedws(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride,
+                   int sms, cudaStream_t stream) {
+  using Cfg = amc::FusedWsCfg<N, CT>;
+  auto kern = amc::fusedws_features_kernel<N, CT>;
+  static thread_local int blocks_per_sm[kMaxDevices] = {};
+  int dev = 0;
+  AMC_CUDA(cudaGetDevice(&dev));
+  if (blocks_per_sm[dev] == 0) {
+    AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int occ = 0;
+    AMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::CTA, Cfg::SMEM_BYTES));
+    if (occ < 1) return fail(AMC_ERR_CUDA, "warp-specialised kernel N=%d does not fit on this device", N);
+    blocks_per_sm[dev] = occ;
+  }
+  const int64_t cap = static_cast<int64_t>(sms) * blocks_per_sm[dev];
+  const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
+  kern<<<grid, Cfg::CTA, Cfg::SMEM_BYTES, stream>>>(static_cast<const CT*>(iq), n_frames, frame_stride, out,
+                                                   out_stride);
+  ++t_launches;
+  AMC_CUDA(cudaGetLastError());
+  return AMC_OK;
+}
+
+template <int N, typename CT>
 int launch_fusedw(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride,
                   int sms, cudaStream_t stream) {
   using Cfg = amc::FusedWCfg<N, CT>;
@@ -169,7 +194,8 @@ int launch_large(const void* iq, int64_t n_frames, int64_t frame_stride, double*
 
 template <typename CT>
 int dispatch_fused(int64_t n, const void* iq, int64_t n_frames, int64_t frame_stride, double* out,
-                   int64_t out_stride, int sms, cudaStream_t stream, bool spt8) {
+                   int64_t out_stride, int sms, cudaStream_t stream, bool spt8, bool ws) {
+  if (ws && n == 2048) return launch_fusedws<2048, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
   if (!spt8) {
     switch (n) {
       case 256: return launch_fusedw<256, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
@@ -322,9 +348,10 @@ int amc_extract_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t fr
     rc = ensure_twiddles(di.dev, stream);
     if (rc != AMC_OK) return rc;
     const bool spt8 = (flags & AMC_FLAG_FUSED_SPT8) != 0;
+    const bool ws = (flags & AMC_FLAG_FUSED_WS) != 0;
     if (iq_dtype == AMC_C128)
-      return dispatch_fused<double2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, spt8);
-    return dispatch_fused<float2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, spt8);
+      return dispatch_fused<double2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, spt8, ws);
+    return dispatch_fused<float2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, spt8, ws);
   }
   if (iq_dtype == AMC_C128)
     return launch_general<double2>(iq, n_frames, frame_size, frame_stride, sample_stride, out, out_stride, di.sms,

@@ -50,13 +50,14 @@ def _stream_ptr(stream):
 
 
 def extract_features(iq, out=None, stream=None, force_general: bool = False, feature_mask: int = nat.AMC_ALL_FEATURES,
-                     spt8: bool = False):
+                     spt8: bool = False, ws: bool = False):
     """All 18 features of every frame of a device-resident complex tensor.
 
     iq  : CUDA tensor (..., frame_size), complex128 or complex64 (north_star's batched entry takes
           (n_snr, n_frames, frame_size)).
     out : optional CUDA float64 tensor (..., 18), C-contiguous.
     spt8: A/B switch - run the first-generation 8-samples-per-thread fused kernel.
+    ws  : A/B switch - run the warp-specialised (FP64 warps / FP32 warps) variant, N = 2048 only.
     Returns float64 (..., 18); column k = feature id k+1.  Enqueued on `stream`
     (default: torch's current stream); does not synchronise.
     """
@@ -73,7 +74,8 @@ def extract_features(iq, out=None, stream=None, force_general: bool = False, fea
         rc = nat.lib().amc_extract_batch(
             x.data_ptr(), _dtype_code(x), n_frames, n, x.stride(0) if n_frames > 1 else n, x.stride(1) if n > 1 else 1,
             out.data_ptr(), N_FEATURES, feature_mask,
-            (nat.AMC_FLAG_FORCE_GENERAL if force_general else 0) | (nat.AMC_FLAG_FUSED_SPT8 if spt8 else 0),
+            (nat.AMC_FLAG_FORCE_GENERAL if force_general else 0) | (nat.AMC_FLAG_FUSED_SPT8 if spt8 else 0)
+            | (nat.AMC_FLAG_FUSED_WS if ws else 0),
             _stream_ptr(stream),
         )
     nat.check(rc)

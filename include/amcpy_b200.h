@@ -55,6 +55,7 @@ extern "C" {
 /* flags */
 #define AMC_FLAG_FORCE_GENERAL 1 /* never take the fused fixed-size kernel */
 #define AMC_FLAG_FUSED_SPT8 2     /* fused kernel variant with 8 samples per thread (kept for N=256 and for A/B runs) */
+#define AMC_FLAG_FUSED_WS 4       /* N = 2048 only: warp-specialised variant (FP64 warps / FP32 warps), A/B runs */
 
 /* return codes */
 #define AMC_OK 0

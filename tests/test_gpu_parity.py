@@ -112,3 +112,18 @@ def test_high_snr_amplitude_features_keep_the_1e9_class(torch_cuda, n, snr_db):
     for fid in (4, 6, 7, 8):
         rel = np.max(np.abs(got[:, fid - 1] - want[:, fid - 1]) / np.abs(want[:, fid - 1]))
         assert rel <= 1e-9, f"feature {fid} at {snr_db} dB, N={n}: rel err {rel:.3e}"
+
+
+def test_warp_specialised_variant_is_bitwise_the_default_kernel(torch_cuda):
+    """AMC_FLAG_FUSED_WS (FP64 warps / FP32 warps, N = 2048) performs the same operations in the same order."""
+    from amcpy_b200 import ops
+
+    x, want = golden_frames(2048)
+    xd = torch_cuda.from_numpy(np.concatenate([x.reshape(-1, 2048)] * 9)).cuda()      # 648 frames: > one wave of CTAs
+    a = ops.extract_features(xd)
+    b = ops.extract_features(xd, ws=True)
+    assert torch_cuda.equal(a, b)
+    assert_features_close(b[:72].cpu().numpy().reshape(want.shape), want)
+    assert torch_cuda.equal(ops.extract_features(xd[:1], ws=True), a[:1])
+    x32 = xd.to(torch_cuda.complex64)
+    assert torch_cuda.equal(ops.extract_features(x32, ws=True), ops.extract_features(x32))
