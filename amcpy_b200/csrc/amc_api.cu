@@ -500,7 +500,10 @@ int amc_extract_host(const void* iq, int iq_dtype, int64_t n_frames, int64_t fra
     cudaStream_t st = p.stream[b];
     cudaError_t e;
     const void* dev_frames = p.d_in[b];
-    if (row_major) {
+    if (row_major && (frame_stride == frame_size || nf == 1)) {   // contiguous rows: one linear copy
+      e = cudaMemcpyAsync(p.d_in[b], src + static_cast<size_t>(f0) * frame_stride * elt,
+                          static_cast<size_t>(nf) * frame_bytes, cudaMemcpyHostToDevice, st);
+    } else if (row_major) {
       e = cudaMemcpy2DAsync(p.d_in[b], frame_bytes, src + static_cast<size_t>(f0) * frame_stride * elt,
                             static_cast<size_t>(frame_stride) * elt, frame_bytes, static_cast<size_t>(nf),
                             cudaMemcpyHostToDevice, st);
@@ -521,9 +524,13 @@ int amc_extract_host(const void* iq, int iq_dtype, int64_t n_frames, int64_t fra
     status = amc_extract_batch(dev_frames, iq_dtype, nf, frame_size, frame_size, 1, p.d_out[b], AMC_N_FEATURES,
                                feature_mask, flags, st);
     if (status != AMC_OK) break;
-    e = cudaMemcpy2DAsync(out + f0 * out_stride, static_cast<size_t>(out_stride) * sizeof(double), p.d_out[b],
-                          AMC_N_FEATURES * sizeof(double), AMC_N_FEATURES * sizeof(double), static_cast<size_t>(nf),
+    if (out_stride == AMC_N_FEATURES)
+      e = cudaMemcpyAsync(out + f0 * out_stride, p.d_out[b], static_cast<size_t>(nf) * AMC_N_FEATURES * sizeof(double),
                           cudaMemcpyDeviceToHost, st);
+    else
+      e = cudaMemcpy2DAsync(out + f0 * out_stride, static_cast<size_t>(out_stride) * sizeof(double), p.d_out[b],
+                            AMC_N_FEATURES * sizeof(double), AMC_N_FEATURES * sizeof(double), static_cast<size_t>(nf),
+                            cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) status = fail(AMC_ERR_CUDA, "device->host copy failed: %s", cudaGetErrorString(e));
   }
   for (int i = 0; i < 2; ++i) {
