@@ -118,7 +118,9 @@ template <int N, typename CT>
 struct Fused16Cfg {
   static constexpr int SPT = 16;
   static constexpr int GROUP = N / SPT;                  // threads per frame: 32..256
-  static constexpr int CTA = GROUP < 128 ? 128 : GROUP;
+  // one frame group per CTA from N = 1024 up (N = 1024: 64 threads, four CTAs per SM - measured 3 % faster than
+  // two 128-thread CTAs holding two groups each); N = 512 keeps four one-warp groups per 128-thread CTA
+  static constexpr int CTA = GROUP < 64 ? 128 : GROUP;
   static constexpr int G = CTA / GROUP;
   static constexpr int W = GROUP / 32;
   static constexpr int SLOT_BYTES = N * static_cast<int>(sizeof(CT));   // one x slot (TMA target)
