@@ -18,7 +18,8 @@ template <int N, typename CT>
 struct FusedWCfg {
   static_assert(N == 256, "warp-per-frame kernel is instantiated for N = 256");
   static constexpr int SPT = 8;
-  static constexpr int CTA = 256, G = 8;                     // 8 warps = 8 frames in flight
+  static constexpr int CTA = 256, G = 8, MIN_BLOCKS = 2;     // 8 warps = 8 frames in flight; smaller CTAs (1-4 warps,
+                                                             // 12-16 warps per SM) were measured 1.5-5 % slower
   static constexpr int SLOT_BYTES = N * static_cast<int>(sizeof(CT));
   static constexpr bool C128 = sizeof(CT) == 16;
   static constexpr int FFTB_BYTES = C128 ? 0 : N * 8;        // c128: both FFT buffers live in the slot
@@ -30,7 +31,7 @@ struct FusedWCfg {
 };
 
 template <int N, typename CT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(FusedWCfg<N, CT>::CTA, FusedWCfg<N, CT>::MIN_BLOCKS)
 fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame_stride,
                        double* __restrict__ out, int64_t out_stride) {
   using Cfg = FusedWCfg<N, CT>;
