@@ -481,7 +481,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     // 16 / M1 butterflies per lane, no twiddles; only max |X_k|^2 is kept
     {
       const float2* rd = tb + (lv >> 4) * (M1 * kTRow) + (lv & 15);
-#pragma unroll 1
+#pragma unroll 1   // (rolled: unrolling it is not faster and costs 1.3 KB of an already oversized loop body)
       for (int bb = 0; bb < 16 / M1; ++bb, rd += 2 * M1 * kTRow) {
         float2 u[M1];
 #pragma unroll
