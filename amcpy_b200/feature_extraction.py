@@ -12,7 +12,8 @@ the library's chunked copy/compute pipeline, and the modulations are spread over
 (one host thread per GPU; under torchrun one rank per GPU takes every world_size-th modulation).
 An uncompressed Level-5 file (scipy's `savemat` default) is not even parsed by scipy: `matio.read_planar`
 memory-maps the separately stored real / imaginary planes and the GPU interleaves them
-(`ops.extract_features_host_planar`); compressed (`save -v7`) files go through `scipy.io.loadmat`.
+(`ops.extract_features_host_planar`); compressed (`save -v7`) variables are inflated in parallel by `matio`
+and take the same route.  `scipy.io.loadmat` is only the I/O fallback for files `matio` cannot parse.
 Deliberate deviations from the reference: shape mismatches and per-modulation
 failures raise instead of being printed over, and elapsed (not CPU) time is reported.
 """
@@ -99,9 +100,9 @@ class _MatSource:
     """The input file, parsed once: memory-mapped planes when the file allows it, scipy.io.loadmat otherwise
     (loaded lazily and only if some variable needs it)."""
 
-    def __init__(self, path):
+    def __init__(self, path, only=None):
         self.path = str(path)
-        self.planar = matio.read_planar(self.path) or {}
+        self.planar = matio.read_planar(self.path, only=only) or {}
         self._mat = None
         self._lock = threading.Lock()   # run_extraction uses one host thread per GPU
 
@@ -149,9 +150,9 @@ def run_extraction(cfg: Config) -> None:
     cfg.paths.ensure_dirs()
     rank, world, local_rank = _rank_world()
     mods = list(cfg.signals.modulations_with_noise)
-    data_mat = _MatSource(cfg.paths.mat_data / cfg.paths.mat_filename)
-    if world > 1:  # one rank per GPU: every world_size-th modulation
-        mine = mods[rank::world]
+    mine = mods[rank::world] if world > 1 else mods  # one rank per GPU: every world_size-th modulation
+    data_mat = _MatSource(cfg.paths.mat_data / cfg.paths.mat_filename, only=[cfg.signals.mat_info[m] for m in mine])
+    if world > 1:
         for m in mine:
             _modulation_process(m, cfg, data_mat, device=local_rank)
         if torch.distributed.is_available() and torch.distributed.is_initialized():

@@ -214,9 +214,10 @@ def test_run_extraction_matches_reference_mat_files(torch_cuda, tmp_path):
         assert np.allclose(got[..., cols_1e9], want[..., cols_1e9], rtol=1.2e-7, atol=0), mod
 
 
-def test_run_extraction_same_files_from_compressed_and_uncompressed_input(torch_cuda, tmp_path):
-    """Uncompressed Level-5 input goes through the memory-mapped planar path, compressed input through
-    scipy.io.loadmat: the written feature files must be identical."""
+def test_run_extraction_same_files_from_compressed_and_uncompressed_input(torch_cuda, tmp_path, monkeypatch):
+    """Uncompressed Level-5 input goes through the memory-mapped planar path, compressed input is inflated
+    by matio and takes the same planar path: the written feature files must be identical (and equal to what
+    the scipy.io.loadmat route produces)."""
     import scipy.io
 
     from amcpy_b200 import matio, synth
@@ -225,18 +226,22 @@ def test_run_extraction_same_files_from_compressed_and_uncompressed_input(torch_
 
     data = synth.dataset(SNRS, 3, 2048, 17)
     outs = []
-    for name, compress in (("plain", False), ("zip", True)):
+    for name, compress in (("plain", False), ("zip", True), ("scipy", True)):
+        if name == "scipy":                                  # third leg: the scipy.io.loadmat route
+            monkeypatch.setattr(matio, "read_planar", lambda path, **kw: None)
         cfg = Config(paths=Paths(root=tmp_path / name), signals=SignalConfig(num_frames=3))
         cfg.paths.ensure_dirs()
         path = cfg.paths.mat_data / cfg.paths.mat_filename
         scipy.io.savemat(str(path), {cfg.signals.mat_info[m]: data[i] for i, m in enumerate(synth.MODULATIONS)},
                          do_compression=compress)
-        assert (matio.read_planar(path) is None) == compress
+        if name != "scipy":
+            assert set(matio.read_planar(path)) == set(cfg.signals.mat_info.values())
         run_extraction(cfg)
         outs.append({m: scipy.io.loadmat(str(cfg.paths.calculated_features / f"{m}_features.mat"))[cfg.signals.mat_info[m]]
                      for m in cfg.signals.modulations_with_noise})
     for m in outs[0]:
         assert np.array_equal(outs[0][m], outs[1][m], equal_nan=True), m
+        assert np.array_equal(outs[0][m], outs[2][m], equal_nan=True), m
 
 
 def test_run_extraction_fails_loudly_on_short_data(torch_cuda, tmp_path):

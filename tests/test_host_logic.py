@@ -149,7 +149,7 @@ def test_features_module_surface():
 
 def test_matio_planar_reader_matches_scipy_and_knows_its_limits(tmp_path):
     """matio.read_planar returns zero-copy planes that reassemble to exactly what scipy.io.loadmat returns;
-    compressed files and non-float variables are left to scipy (I/O fallback only)."""
+    compressed variables are inflated (in parallel) and parsed the same way; non-float variables are skipped."""
     import scipy.io
 
     from amcpy_b200 import matio
@@ -174,7 +174,22 @@ def test_matio_planar_reader_matches_scipy_and_knows_its_limits(tmp_path):
     # element (s, f, n) of the column-major variable = plane[s + S*f + S*F*n]
     S, F, _ = a.shape
     assert got["signal_qpsk"].re[3 + S * 2 + S * F * 10] == a[3, 2, 10].real
-    scipy.io.savemat(str(p), {"signal_qpsk": a}, do_compression=True)
-    assert matio.read_planar(p) is None
+    # compressed elements (`save -v7` / do_compression=True): same planes, views of the inflated buffers
+    scipy.io.savemat(str(p), {"signal_qpsk": a, "signal_bpsk": b, "real": c, "Modulation": "QPSK"}, do_compression=True)
+    got = matio.read_planar(p, max_workers=2)
+    ref = scipy.io.loadmat(str(p))
+    assert set(got) == {"signal_qpsk", "signal_bpsk", "real"}
+    for k in got:
+        q = got[k]
+        full = q.re.reshape(q.shape, order="F")
+        if q.im is not None:
+            full = full + 1j * q.im.reshape(q.shape, order="F")
+        assert q.shape == ref[k].shape and np.array_equal(full, ref[k]), k
+    assert set(matio.read_planar(p, only=["signal_bpsk"])) == {"signal_bpsk"}
+    # a damaged zlib stream skips that variable (the caller then asks scipy, which raises)
+    raw = bytearray(p.read_bytes())
+    raw[128 + 8 + 20:128 + 8 + 40] = bytes(20)
+    (tmp_path / "bad.mat").write_bytes(bytes(raw))
+    assert len(matio.read_planar(tmp_path / "bad.mat")) < 3
     (tmp_path / "junk.mat").write_bytes(b"not a mat file")
     assert matio.read_planar(tmp_path / "junk.mat") is None
