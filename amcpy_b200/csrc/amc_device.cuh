@@ -339,6 +339,13 @@ __device__ __noinline__ void finalize_features(const FrameSums& fs, int n, doubl
     c.re += 18.0 * m.m21 * abs20sq;
     out[17] = cabs(c);
   }
+  // A NaN anywhere in the frame reaches all 18 features of the reference (through the FFT, the means and the
+  // sums).  The GPU's min/max instructions drop NaNs (spectral max, tie detection), so the rule is applied here:
+  // sum a^2 + sum b^2 is NaN if and only if some sample holds a NaN (infinities and overflow give +inf).
+  if (isnan(fs.mono[0] + fs.mono[1])) {
+#pragma unroll
+    for (int i = 0; i < 18; ++i) out[i] = nan;
+  }
 }
 
 }  // namespace amc

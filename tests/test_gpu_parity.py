@@ -100,9 +100,10 @@ def test_exact_zeros_octant_points_and_signed_zero(torch_cuda, n):
 @pytest.mark.parametrize("n", [256, 2048])
 @pytest.mark.parametrize("snr_db", [30.0, 40.0, 50.0])
 def test_high_snr_amplitude_features_keep_the_1e9_class(torch_cuda, n, snr_db):
-    """sum (r-mu)^2 is derived from sum|x|^2 and sum|x| in the fused kernels (cancellation ~ (mu/sigma)^2 ulps):
-    the amplitude features (4 std of |cn|, 8 kurtosis of cn) must still meet 1e-9 against the two-pass oracle on
-    nearly constant-modulus frames, far above the reference's own SNR grid (<= 20 dB)."""
+    """The amplitude features (4 std of |cn|, 8 kurtosis of cn) must meet 1e-9 against the two-pass oracle on
+    nearly constant-modulus frames, far above the reference's own SNR grid (<= 20 dB).  (Deriving sum (r-mu)^2
+    from sum|x|^2 and sum|x| - one FP64 operation per sample cheaper - fails this test: cancellation
+    ~ (mu/sigma)^2 ulps; the kernels accumulate the centred sums explicitly.)"""
     from amcpy_b200 import ops, synth
     from oracle import amc_oracle as orc
 
@@ -112,6 +113,30 @@ def test_high_snr_amplitude_features_keep_the_1e9_class(torch_cuda, n, snr_db):
     for fid in (4, 6, 7, 8):
         rel = np.max(np.abs(got[:, fid - 1] - want[:, fid - 1]) / np.abs(want[:, fid - 1]))
         assert rel <= 1e-9, f"feature {fid} at {snr_db} dB, N={n}: rel err {rel:.3e}"
+
+
+@pytest.mark.parametrize("n", [100, 256, 1024, 2048, 4096, 16384])
+def test_nan_samples_poison_their_frame_and_only_their_frame(torch_cuda, n):
+    """A NaN anywhere in a frame makes all 18 reference features NaN (FFT, means, sums); GPU min/max
+    instructions drop NaNs, so the kernels apply the rule explicitly.  Neighbouring frames of the same
+    launch (same CTA, same finalisation batch) must be untouched."""
+    from amcpy_b200 import ops
+    from oracle import amc_oracle as orc
+
+    rng = np.random.default_rng(n + 5)
+    x = (rng.standard_normal((40, n)) + 1j * rng.standard_normal((40, n))) * 0.9
+    bad = {3: (0, complex(np.nan, 0.25)), 4: (n - 1, complex(0.5, np.nan)), 17: (n // 2 + 1, complex(np.nan, np.nan)),
+           38: (n // 3, complex(-np.nan, 1.0))}
+    for r, (pos, val) in bad.items():
+        x[r, pos] = val
+    with np.errstate(all="ignore"):
+        want = orc.features_batch(x)
+    assert np.isnan(want[list(bad)]).all() and np.isfinite(np.delete(want, list(bad), axis=0)).all()
+    for force in (False, True):
+        got = ops.extract_features(torch_cuda.from_numpy(x).cuda(), force_general=force).cpu().numpy()
+        assert np.isnan(got[list(bad)]).all(), (n, force)
+        good = np.delete(np.arange(40), list(bad))
+        assert_features_close(got[good], want[good])
 
 
 def test_warp_specialised_variant_is_bitwise_the_default_kernel(torch_cuda):
