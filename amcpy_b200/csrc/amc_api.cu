@@ -103,11 +103,26 @@ int launch_fused(const void* iq, int64_t n_frames, int64_t frame_stride, double*
   return AMC_OK;
 }
 
-template <int N, typename CT>
+// feature_mask -> the cheapest compiled profile of the 16-samples-per-thread kernel that covers it
+// (amc_fused16.cuh: kProf*).  Compiled: moments only, amplitude + moments, everything but the FFT, all.
+int pick_profile(uint32_t feature_mask) {
+  int need = 0;
+  if (feature_mask & 0x00001u) need |= amc::kProfFft;
+  if (feature_mask & 0x00116u) need |= amc::kProfPhase;   // features 2, 3, 5, 9
+  if (feature_mask & 0x000e8u) need |= amc::kProfAmp;     // features 4, 6, 7, 8
+  if (feature_mask & 0x3fe00u) need |= amc::kProfMom;     // features 10..18
+  constexpr int compiled[] = {amc::kProfMom, amc::kProfAmp | amc::kProfMom,
+                              amc::kProfPhase | amc::kProfAmp | amc::kProfMom, amc::kProfAll};
+  for (int p : compiled)
+    if ((p & need) == need) return p;
+  return amc::kProfAll;
+}
+
+template <int N, typename CT, int PROF = amc::kProfAll>
 int launch_fused16(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride,
                    int sms, cudaStream_t stream) {
   using Cfg = amc::Fused16Cfg<N, CT>;
-  auto kern = amc::fused16_features_kernel<N, CT>;
+  auto kern = amc::fused16_features_kernel<N, CT, PROF>;
   static thread_local int blocks_per_sm[kMaxDevices] = {};
   int dev = 0;
   AMC_CUDA(cudaGetDevice(&dev));
@@ -192,10 +207,35 @@ int launch_large(const void* iq, int64_t n_frames, int64_t frame_stride, double*
   return AMC_OK;
 }
 
+template <int N, typename CT>
+int launch_fused16_profile(int prof, const void* iq, int64_t n_frames, int64_t frame_stride, double* out,
+                           int64_t out_stride, int sms, cudaStream_t stream) {
+  switch (prof) {
+    case amc::kProfMom:
+      return launch_fused16<N, CT, amc::kProfMom>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+    case amc::kProfAmp | amc::kProfMom:
+      return launch_fused16<N, CT, amc::kProfAmp | amc::kProfMom>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+    case amc::kProfPhase | amc::kProfAmp | amc::kProfMom:
+      return launch_fused16<N, CT, amc::kProfPhase | amc::kProfAmp | amc::kProfMom>(iq, n_frames, frame_stride, out,
+                                                                                     out_stride, sms, stream);
+    default:
+      return launch_fused16<N, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+  }
+}
+
 template <typename CT>
 int dispatch_fused(int64_t n, const void* iq, int64_t n_frames, int64_t frame_stride, double* out,
-                   int64_t out_stride, int sms, cudaStream_t stream, bool spt8, bool ws) {
+                   int64_t out_stride, int sms, cudaStream_t stream, bool spt8, bool ws, int prof) {
   if (ws && n == 2048) return launch_fusedws<2048, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+  if (!spt8 && prof != amc::kProfAll) {   // reduced feature profiles exist for the 16-samples-per-thread kernel only
+    switch (n) {
+      case 512: return launch_fused16_profile<512, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 1024: return launch_fused16_profile<1024, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 2048: return launch_fused16_profile<2048, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 4096: return launch_fused16_profile<4096, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      default: break;
+    }
+  }
   if (!spt8) {
     switch (n) {
       case 256: return launch_fusedw<256, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
@@ -349,9 +389,12 @@ int amc_extract_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t fr
     if (rc != AMC_OK) return rc;
     const bool spt8 = (flags & AMC_FLAG_FUSED_SPT8) != 0;
     const bool ws = (flags & AMC_FLAG_FUSED_WS) != 0;
+    const int prof = pick_profile(feature_mask);
     if (iq_dtype == AMC_C128)
-      return dispatch_fused<double2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, spt8, ws);
-    return dispatch_fused<float2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, spt8, ws);
+      return dispatch_fused<double2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, spt8, ws,
+                                     prof);
+    return dispatch_fused<float2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, spt8, ws,
+                                  prof);
   }
   if (iq_dtype == AMC_C128)
     return launch_general<double2>(iq, n_frames, frame_size, frame_stride, sample_stride, out, out_stride, di.sms,

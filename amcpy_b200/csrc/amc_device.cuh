@@ -199,7 +199,7 @@ struct Monomials {
     s[12] = b4 * a2;
     s[13] = b4 * ab;
     s[14] = b4 * b2;
-    return a2 + b2;
+    return __dadd_rn(a2, b2);   // never contracted: the reduced feature profiles form |x|^2 the same way
   }
   // returns a*a + b*b
   __device__ __forceinline__ double add(double a, double b) {
@@ -220,7 +220,7 @@ struct Monomials {
     s[12] = fma(b4, a2, s[12]);
     s[13] = fma(b4, ab, s[13]);
     s[14] = fma(b4, b2, s[14]);
-    return a2 + b2;
+    return __dadd_rn(a2, b2);   // never contracted: the reduced feature profiles form |x|^2 the same way
   }
 };
 

@@ -111,6 +111,15 @@ __global__ void init_twiddle16dif_kernel() {
 // conflict-free exchange layout for the 16 x 16 x R Stockham passes: low 4 bits ^= bits 4..7
 __device__ __forceinline__ int swz16(int e) { return e ^ ((e >> 4) & 15); }
 
+// Feature groups one instantiation of the kernel computes.  The C ABI's feature_mask picks the cheapest compiled
+// profile that covers the requested features (amc_api.cu: pick_profile); columns of groups that were not
+// computed are written as NaN.  kProfAll is the drop-in default (and the benchmarked kernel).
+constexpr int kProfFft = 1;     // feature 1            (spectral max: the three FFT stages)
+constexpr int kProfPhase = 2;   // features 2, 3, 5, 9  (atan2, wrapped differences, phase / frequency statistics)
+constexpr int kProfAmp = 4;     // features 4, 6, 7, 8  (|x| in FP64, centred amplitude sums)
+constexpr int kProfMom = 8;     // features 10..18      (the 15 monomial sums)
+constexpr int kProfAll = 15;
+
 constexpr int kTRow = 17;         // float2 per lane row of the warp-private exchange buffer (16 + 1 pad)
 constexpr int kPend16Stride = 25; // doubles per parked frame (25 totals; odd stride: conflict-free lane-per-frame reads)
 
@@ -151,12 +160,15 @@ struct Fused16Cfg {
   static_assert(F * W == 16, "16 sub-transforms per frame");
 };
 
-template <int N, typename CT>
+template <int N, typename CT, int PROF = kProfAll>
 __global__ void __launch_bounds__(Fused16Cfg<N, CT>::CTA, Fused16Cfg<N, CT>::MIN_BLOCKS)
 fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame_stride,
                         double* __restrict__ out, int64_t out_stride) {
   using Cfg = Fused16Cfg<N, CT>;
   constexpr int GROUP = Cfg::GROUP, W = Cfg::W, SPT = Cfg::SPT, M1 = Cfg::M1, LOG_M1 = Cfg::LOG_M1;
+  constexpr bool DO_FFT = (PROF & kProfFft) != 0, DO_PHASE = (PROF & kProfPhase) != 0, DO_AMP = (PROF & kProfAmp) != 0,
+                 DO_MOM = (PROF & kProfMom) != 0;
+  static_assert(PROF > 0 && PROF <= kProfAll, "unknown feature profile");
   extern __shared__ __align__(128) unsigned char smem_raw[];
 
   const int tid = threadIdx.x;
@@ -236,7 +248,18 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         fs.mean_f = pl[23] / (N - 1);
         fs.spec_max = pl[24];
         const int64_t fo = gg + static_cast<int64_t>(k - bi + lane) * tg;
-        finalize_features(fs, N, out + fo * out_stride);
+        double* row = out + fo * out_stride;
+        finalize_features(fs, N, row);
+        if constexpr (PROF != kProfAll) {              // groups this profile did not compute
+          const double nan = __longlong_as_double(0x7ff8000000000000LL);
+          if (!DO_FFT) row[0] = nan;
+          if (!DO_PHASE) row[1] = row[2] = row[4] = row[8] = nan;
+          if (!DO_AMP) row[3] = row[5] = row[6] = row[7] = nan;
+          if (!DO_MOM) {
+#pragma unroll
+            for (int i = 9; i < 18; ++i) row[i] = nan;
+          }
+        }
       }
       __syncwarp();
     }
@@ -264,20 +287,30 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     for (int j = 0; j < SPT; ++j) {
       double a, b;
       load_sample<CT>(xs + t + GROUP * j, a, b, xr[j], xi[j]);
-#ifndef AMC_EXP_NO_FP64
-      const double s = (j == 0) ? mono.init(a, b) : mono.add(a, b);
-      r[j] = sqrt_nr(s);
-#else
-      if (j == 0) mono.clear();
-      r[j] = a + b;
-#endif
-      sum_r = (j == 0) ? r[j] : sum_r + r[j];
-#ifndef AMC_EXP_NO_PHASE
-      ph[j] = atan2_fast(xi[j], xr[j]);
-#else
-      ph[j] = xi[j] + xr[j];
-#endif
+      double s = 0.0;
+      if constexpr (DO_MOM) {
+        s = (j == 0) ? mono.init(a, b) : mono.add(a, b);
+      } else {
+        if (j == 0) mono.clear();
+        if constexpr (DO_AMP) s = __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));   // as Monomials::add forms it
+      }
+      if constexpr (DO_AMP) {
+        r[j] = sqrt_nr(s);
+        sum_r = (j == 0) ? r[j] : sum_r + r[j];
+      } else {
+        r[j] = 0.0;
+        sum_r = 0.0;
+      }
+      if constexpr (DO_PHASE) ph[j] = atan2_fast(xi[j], xr[j]);
+      else ph[j] = 0.0f;
     }
+    float fq[SPT];                                             // unwrapped phase steps in RADIANS (scaled in park)
+    float s_ph = 0.0f, s_aph = 0.0f, s_f = 0.0f;
+    const float last_keep = (t == GROUP - 1) ? 0.0f : 1.0f;   // sample N-1 has no successor
+    if constexpr (!DO_PHASE) {
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) fq[j] = 0.0f;
+    } else {
     // phase of the sample after this warp's run of 32, for every j: lane j evaluates it, lane 31 uses it
     if (lane < SPT) {
       const int te = opaque_if<Cfg::REG_BOUND>(t);
@@ -294,10 +327,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     __syncwarp();
     // wrapped phase differences (np.unwrap); differences within kTieEps of +-pi are only flagged
     // here and re-decided in FP64 after the loop, so the hot loop stays branch-free
-    float fq[SPT];                                             // unwrapped phase steps in RADIANS (scaled in park)
-    float s_ph = 0.0f, s_aph = 0.0f;
     float tie_min = 1.0f;                                      // min | |dd| - pi | over this thread's steps
-    const float last_keep = (t == GROUP - 1) ? 0.0f : 1.0f;   // sample N-1 has no successor
     float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
@@ -330,9 +360,9 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         for (int q = 0; q < SPT; ++q) fq[q] = (q == j) ? val : fq[q];
       }
     }
-    float s_f = 0.0f;
 #pragma unroll
     for (int j = 0; j < SPT; ++j) s_f += fq[j];
+    }   // DO_PHASE
     {
       // 16 FP64 partials per lane -> 16 warp totals: transposed through the warp-private buffer
       // (16 STS.64 + 16 LDS.64 + 16 DADD; the shuffle butterfly needed 60 selects + 32 shuffles)
@@ -366,8 +396,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     float2 v[16];
     const int tv = opaque_if<Cfg::REG_BOUND>(t);          // keeps the geometry below out of pass 1
     const int lv = tv & 31, wv = tv >> 5;
-#ifndef AMC_EXP_NO_FFT
-    {
+    if constexpr (DO_FFT) {
       const int rot_t = (((tv & 15) << (4 - LOG_M1)) | ((tv & 15) >> LOG_M1)) & 15;
       const uint32_t row_a = (smem_u32(buf_a) + 128u * tv) ^ (8u * rot_t);   // row start is 128-byte aligned
 #pragma unroll
@@ -391,7 +420,6 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(row_a ^ (8u * q)), "f"(o.x), "f"(o.y) : "memory");
       }
     }
-#endif
 
     group_sync<GROUP, Cfg::CTA>(g);   // THE barrier: pass-1 partials + stage-A output visible; x slot fully read
 
@@ -425,23 +453,27 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int j = 0; j < SPT; ++j) {
-        const double d = r[j] - mu_r;
-        const double d2 = d * d;
-        c2acc[0] += fabs(d);
-        c2acc[1] += d2;
-        c2acc[2] = fma(d2, d2, c2acc[2]);
-        const float e = ph[j] - mu_ph;
-        q2acc[0] = fmaf(e, e, q2acc[0]);
-        const float ea = fabsf(ph[j]) - mu_aph;
-        q2acc[1] = fmaf(ea, ea, q2acc[1]);
-        float ef = fq[j] - mu_f;
-        if (j == SPT - 1) ef *= last_keep;
-        const float ef2 = ef * ef;
-        q2acc[2] += ef2;
-        q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
+        if constexpr (DO_AMP) {
+          const double d = r[j] - mu_r;
+          const double d2 = d * d;
+          c2acc[0] += fabs(d);
+          c2acc[1] += d2;
+          c2acc[2] = fma(d2, d2, c2acc[2]);
+        }
+        if constexpr (DO_PHASE) {
+          const float e = ph[j] - mu_ph;
+          q2acc[0] = fmaf(e, e, q2acc[0]);
+          const float ea = fabsf(ph[j]) - mu_aph;
+          q2acc[1] = fmaf(ea, ea, q2acc[1]);
+          float ef = fq[j] - mu_f;
+          if (j == SPT - 1) ef *= last_keep;
+          const float ef2 = ef * ef;
+          q2acc[2] += ef2;
+          q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
+        }
       }
-      warp_sum_multi<double, 4>(c2acc, lane);
-      warp_sum_multi<float, 4>(q2acc, lane);
+      if constexpr (DO_AMP) warp_sum_multi<double, 4>(c2acc, lane);
+      if constexpr (DO_PHASE) warp_sum_multi<float, 4>(q2acc, lane);
       if ((lane & 7) == 0) {
         if (lane < 24) part_d(par, wg)[16 + (lane >> 3)] = c2acc[0];
         part_d(par, wg)[19 + (lane >> 3)] = static_cast<double>(q2acc[0]);
@@ -449,9 +481,10 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     }
 
     float vmax = 0.0f;
-#ifdef AMC_EXP_NO_FFT
-    vmax = xr[0] + xi[15];
-#else
+    if constexpr (!DO_FFT) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rbar);   // this warp's reads of the parked partials are done
+    } else {
     // ---------------------------------------------------------------- FFT stage B: this warp owns the
     // sub-transforms k1 = wg F .. wg F + F-1 (each GROUP points, n1 = m1 + M1 m2); lane (f, m1) does the
     // radix-16 over m2 and applies W_GROUP^(m1 q)
@@ -501,8 +534,8 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         for (int q = 0; q < M1; ++q) vmax = fmaxf(vmax, fmaf(u[q].x, u[q].x, u[q].y * u[q].y));
       }
     }
-#endif
     vmax = warp_max(vmax);
+    }   // DO_FFT
     if (lane == 0) part_d(par, wg)[24] = static_cast<double>(vmax);
     // no barrier here: buf_a and the partial arrays are protected by rbar (waited on in the next frame's
     // pass 1); the warp-private buffer is only touched by this warp

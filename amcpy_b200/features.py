@@ -41,13 +41,13 @@ def _to_device_frame(signal):
     return torch.from_numpy(np.ascontiguousarray(a).reshape(1, -1)).cuda()
 
 
-def _all18(signal) -> np.ndarray:
-    return ops.extract_features(_to_device_frame(signal)).cpu().numpy().reshape(18)
+def _all18(signal, feature_mask: int = ops.nat.AMC_ALL_FEATURES) -> np.ndarray:
+    return ops.extract_features(_to_device_frame(signal), feature_mask=feature_mask).cpu().numpy().reshape(18)
 
 
 def _make(fid: int, name: str):
     def fn(signal) -> float:
-        return float(_all18(signal)[fid - 1])
+        return float(_all18(signal, 1 << (fid - 1))[fid - 1])
 
     fn.__name__ = name
     fn.__qualname__ = name
@@ -68,7 +68,7 @@ def calculate_features(feature_ids, signal) -> list:
         _FEATURE_FUNCTIONS[fid]  # KeyError on unknown id, like the reference's dict lookup
     if not ids:
         return []
-    row = _all18(signal)
+    row = _all18(signal, ops.feature_mask_of(ids))   # feature groups nobody asked for may be skipped
     return [float(row[fid - 1]) for fid in ids]
 
 
@@ -81,11 +81,12 @@ def calculate_features_batch(feature_ids, frames):
     for fid in ids:
         _FEATURE_FUNCTIONS[fid]
     cols = [fid - 1 for fid in ids]
+    mask = ops.feature_mask_of(ids) if ids else ops.nat.AMC_ALL_FEATURES
     if isinstance(frames, torch.Tensor):
-        return ops.extract_features(frames)[..., cols]
+        return ops.extract_features(frames, feature_mask=mask)[..., cols]
     a = np.asarray(frames)
     lead = a.shape[:-1]
-    res = ops.extract_features_host(a.reshape(-1, a.shape[-1]))
+    res = ops.extract_features_host(a.reshape(-1, a.shape[-1]), feature_mask=mask)
     return res[:, cols].reshape(lead + (len(cols),))
 
 

@@ -49,9 +49,23 @@ def _stream_ptr(stream):
     return s.cuda_stream
 
 
+def feature_mask_of(feature_ids) -> int:
+    """C-ABI feature_mask (bit k = feature id k+1) of a list of ids 1..18."""
+    mask = 0
+    for fid in feature_ids:
+        if not 1 <= int(fid) <= N_FEATURES:
+            raise KeyError(fid)
+        mask |= 1 << (int(fid) - 1)
+    return mask
+
+
 def extract_features(iq, out=None, stream=None, force_general: bool = False, feature_mask: int = nat.AMC_ALL_FEATURES,
                      spt8: bool = False, ws: bool = False):
     """All 18 features of every frame of a device-resident complex tensor.
+
+    feature_mask (default: all 18): the features the caller will read.  The library may skip the work of
+    feature groups outside the mask (FFT / phase+frequency / amplitude / moments; frame sizes 512..4096); the
+    columns of a skipped group hold NaN, requested columns are bitwise what the full call returns.
 
     iq  : CUDA tensor (..., frame_size), complex128 or complex64 (north_star's batched entry takes
           (n_snr, n_frames, frame_size)).
@@ -91,7 +105,7 @@ def _np_dtype_code(a: np.ndarray) -> int:
 
 
 def extract_features_host(frames: np.ndarray, device: int = 0, out: np.ndarray | None = None,
-                          force_general: bool = False) -> np.ndarray:
+                          force_general: bool = False, feature_mask: int = nat.AMC_ALL_FEATURES) -> np.ndarray:
     """Host arrays through the library's chunked copy/compute pipeline (amc_extract_host).
 
     frames: (n_frames, N) complex array.  Row-per-frame (C order, rows may be padded) and
@@ -122,7 +136,7 @@ def extract_features_host(frames: np.ndarray, device: int = 0, out: np.ndarray |
     elif out.dtype != np.float64 or out.shape != (nf, N_FEATURES) or not out.flags.c_contiguous:
         raise ValueError("out must be C-contiguous float64 (n_frames, 18)")
     rc = nat.lib().amc_extract_host(
-        a.ctypes.data, code, nf, n, s0, s1, out.ctypes.data, N_FEATURES, nat.AMC_ALL_FEATURES,
+        a.ctypes.data, code, nf, n, s0, s1, out.ctypes.data, N_FEATURES, feature_mask,
         nat.AMC_FLAG_FORCE_GENERAL if force_general else 0, device,
     )
     nat.check(rc)

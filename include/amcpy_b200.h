@@ -79,8 +79,11 @@ int amc_device_count(void);
  * synchronise, does not allocate.
  *   iq           device pointer, complex64/complex128 interleaved
  *   out          device pointer, float64, row f at out + f*out_stride, out_stride >= 18
- *   feature_mask bit k = feature k+1 wanted; all 18 columns are always written (a cleared bit
- *                only lets the library skip work in a later revision); must be non-zero
+ *   feature_mask bit k = feature k+1 wanted; must be non-zero.  All 18 columns are always written: a wanted
+ *                column holds the feature (bitwise the value an all-features call returns); an unwanted
+ *                column holds either the feature or NaN - the library skips whole feature groups nobody
+ *                asked for (FFT: 1; phase/frequency: 2,3,5,9; amplitude: 4,6,7,8; moments: 10..18) where a
+ *                reduced kernel profile exists (frame sizes 512..4096).  AMC_ALL_FEATURES = the drop-in.
  * n_frames == 0 is a no-op.
  */
 int amc_extract_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size,

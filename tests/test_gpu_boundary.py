@@ -257,6 +257,60 @@ def test_run_extraction_fails_loudly_on_short_data(torch_cuda, tmp_path):
         run_extraction(cfg)
 
 
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+@pytest.mark.parametrize("dtype", ["c128", "c64"])
+def test_feature_mask_profiles_skip_work_not_accuracy(torch_cuda, n, dtype):
+    """feature_mask of the C ABI: requested columns are BITWISE what the all-features call returns, columns of
+    feature groups the library skipped hold NaN (frame sizes 512..4096 have reduced profiles: moments only,
+    amplitude + moments, everything but the FFT)."""
+    from amcpy_b200 import ops
+
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((70, n)) + 1j * rng.standard_normal((70, n))) * 0.8
+    xd = torch_cuda.from_numpy(x.astype(np.complex64) if dtype == "c64" else x).cuda()
+    full = ops.extract_features(xd).cpu().numpy()
+    assert np.isfinite(full).all()
+    groups = {"fft": [1], "phase": [2, 3, 5, 9], "amp": [4, 6, 7, 8], "mom": list(range(10, 19))}
+    cases = [
+        ([10, 12, 18], {"mom"}),                          # moments only
+        ([14], {"mom"}),
+        ([6, 13], {"amp", "mom"}),                        # amplitude + moments
+        ([4, 7, 8], {"amp", "mom"}),                      # (cheapest compiled superset)
+        ([2, 4, 6, 8, 12, 14], {"phase", "amp", "mom"}),  # the reference's default feature list: no FFT
+        ([3, 5, 7, 9, 13, 15], {"phase", "amp", "mom"}),
+        ([9], {"phase", "amp", "mom"}),
+        ([1], {"fft", "phase", "amp", "mom"}),            # anything with feature 1: the full kernel
+        (list(range(1, 19)), {"fft", "phase", "amp", "mom"}),
+    ]
+    for ids, computed in cases:
+        got = ops.extract_features(xd, feature_mask=ops.feature_mask_of(ids)).cpu().numpy()
+        for name, fids in groups.items():
+            cols = [f - 1 for f in fids]
+            if name in computed:
+                assert np.array_equal(got[:, cols], full[:, cols]), (ids, name)
+            else:
+                assert np.isnan(got[:, cols]).all(), (ids, name)
+    # the batched operator API passes the mask of the ids it returns
+    from amcpy_b200 import features as F
+    sel = F.calculate_features_batch([12, 14, 10], xd).cpu().numpy()
+    assert np.array_equal(sel, full[:, [11, 13, 9]])
+    sel_h = F.calculate_features_batch([2, 6], np.ascontiguousarray(xd.cpu().numpy()))
+    assert np.array_equal(sel_h, full[:, [1, 5]])
+
+
+def test_feature_mask_is_ignored_where_no_reduced_profile_exists(torch_cuda):
+    from amcpy_b200 import ops
+
+    rng = np.random.default_rng(1)
+    for n in (100, 256, 8192):
+        x = torch_cuda.from_numpy(rng.standard_normal((5, n)) + 1j * rng.standard_normal((5, n))).cuda()
+        full = ops.extract_features(x).cpu().numpy()
+        got = ops.extract_features(x, feature_mask=ops.feature_mask_of([10, 11])).cpu().numpy()
+        assert np.array_equal(got, full)
+    with pytest.raises(KeyError):
+        ops.feature_mask_of([0])
+
+
 # ------------------------------------------------------------------ C ABI error behaviour
 def test_c_abi_error_codes(torch_cuda):
     from amcpy_b200 import _native as nat
