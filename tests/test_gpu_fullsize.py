@@ -165,3 +165,22 @@ def test_repeated_launches_are_bitwise_identical(n, frames):
         assert torch.equal(got, ref), f"launch {i} differs"
     torch.cuda.synchronize()
     assert torch.equal(other, ref[: frames // 2])
+
+
+@pytest.mark.parametrize("n,frames", [(512, 40000), (2048, 48000), (4096, 6000)])
+def test_feature_profiles_bitwise_on_long_runs(n, frames):
+    """Reduced feature profiles (feature_mask) over many frames per CTA: the requested columns stay bitwise what
+    the all-features kernel returns, launch after launch (their barrier / mbarrier placement differs from the
+    full kernel's, so this is also their race check)."""
+    import torch
+
+    from amcpy_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(n + 1)
+    x = torch.randn((frames, n), dtype=torch.complex128, device="cuda", generator=g)
+    full = ops.extract_features(x).clone()
+    for ids in ([10, 11, 12, 13, 14, 15, 16, 17, 18], [4, 6, 7, 8, 16], [2, 4, 6, 8, 12, 14]):
+        cols = [i - 1 for i in ids]
+        for rep in range(4):
+            got = ops.extract_features(x, feature_mask=ops.feature_mask_of(ids))
+            assert torch.equal(got[:, cols], full[:, cols]), (ids, rep)

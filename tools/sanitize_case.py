@@ -15,3 +15,10 @@ for n, frames in ((2048, 700), (256, 3000), (512, 900), (1024, 500), (4096, 300)
     print(n, bool(torch.isfinite(a).all()))
 x = torch.randn((300, 2048), dtype=torch.complex64, device="cuda", generator=g)
 print("c64", bool(torch.isfinite(ops.extract_features(x)).all()))
+# reduced feature profiles of the 16-samples-per-thread kernel (different barrier / mbarrier placement without the FFT)
+for ids in ([10, 18], [6, 12], [2, 4, 6, 8, 12, 14]):
+    for n, frames in ((2048, 700), (512, 900), (4096, 300)):
+        x = torch.randn((frames, n), dtype=torch.complex128, device="cuda", generator=g)
+        a = ops.extract_features(x, feature_mask=ops.feature_mask_of(ids))
+        torch.cuda.synchronize()
+        print(ids, n, bool(torch.isfinite(a[:, [i - 1 for i in ids]]).all()))
