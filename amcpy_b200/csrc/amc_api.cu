@@ -167,11 +167,11 @@ int launch_fusedws(const void* iq, int64_t n_frames, int64_t frame_stride, doubl
   return AMC_OK;
 }
 
-template <int N, typename CT>
+template <int N, typename CT, int PROF = amc::kProfAll>
 int launch_fusedw(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride,
                   int sms, cudaStream_t stream) {
   using Cfg = amc::FusedWCfg<N, CT>;
-  auto kern = amc::fusedw_features_kernel<N, CT>;
+  auto kern = amc::fusedw_features_kernel<N, CT, PROF>;
   static thread_local int blocks_per_sm[kMaxDevices] = {};
   int dev = 0;
   AMC_CUDA(cudaGetDevice(&dev));
@@ -227,7 +227,14 @@ template <typename CT>
 int dispatch_fused(int64_t n, const void* iq, int64_t n_frames, int64_t frame_stride, double* out,
                    int64_t out_stride, int sms, cudaStream_t stream, bool spt8, bool ws, int prof) {
   if (ws && n == 2048) return launch_fusedws<2048, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-  if (!spt8 && prof != amc::kProfAll) {   // reduced feature profiles exist for the 16-samples-per-thread kernel only
+  if (!spt8 && prof != amc::kProfAll) {   // reduced feature profiles: warp-per-frame and 16-samples-per-thread kernels
+    constexpr int kAM = amc::kProfAmp | amc::kProfMom, kPAM = amc::kProfPhase | kAM;
+    if (n == 256) {
+      if (prof == amc::kProfMom)
+        return launch_fusedw<256, CT, amc::kProfMom>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      if (prof == kAM) return launch_fusedw<256, CT, kAM>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      if (prof == kPAM) return launch_fusedw<256, CT, kPAM>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+    }
     switch (n) {
       case 512: return launch_fused16_profile<512, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream);
       case 1024: return launch_fused16_profile<1024, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream);

@@ -236,6 +236,15 @@ __device__ __forceinline__ Cplx csub(Cplx a, Cplx b) { return {a.re - b.re, a.im
 __device__ __forceinline__ Cplx cconj(Cplx a) { return {a.re, -a.im}; }
 __device__ __forceinline__ double cabs(Cplx a) { return hypot(a.re, a.im); }
 
+// Feature groups one instantiation of a fused kernel computes (amc_fused16.cuh, amc_fusedw.cuh).  The C ABI's feature_mask picks the cheapest compiled
+// profile that covers the requested features (amc_api.cu: pick_profile); columns of groups that were not
+// computed are written as NaN.  kProfAll is the drop-in default (and the benchmarked kernel).
+constexpr int kProfFft = 1;     // feature 1            (spectral max: the three FFT stages)
+constexpr int kProfPhase = 2;   // features 2, 3, 5, 9  (atan2, wrapped differences, phase / frequency statistics)
+constexpr int kProfAmp = 4;     // features 4, 6, 7, 8  (|x| in FP64, centred amplitude sums)
+constexpr int kProfMom = 8;     // features 10..18      (the 15 monomial sums)
+constexpr int kProfAll = 15;
+
 // The eleven mixed moments from the (already /N) monomial means (features.py:46-58).
 struct Moments {
   Cplx m20, m22, m40, m41, m43, m60, m61, m63;
@@ -345,6 +354,21 @@ __device__ __noinline__ void finalize_features(const FrameSums& fs, int n, doubl
   if (isnan(fs.mono[0] + fs.mono[1])) {
 #pragma unroll
     for (int i = 0; i < 18; ++i) out[i] = nan;
+  }
+}
+
+// columns of the feature groups a reduced profile did not compute
+template <int PROF>
+__device__ __forceinline__ void blank_skipped_groups(double* __restrict__ row) {
+  if constexpr (PROF != kProfAll) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (!(PROF & kProfFft)) row[0] = nan;
+    if (!(PROF & kProfPhase)) row[1] = row[2] = row[4] = row[8] = nan;
+    if (!(PROF & kProfAmp)) row[3] = row[5] = row[6] = row[7] = nan;
+    if (!(PROF & kProfMom)) {
+#pragma unroll
+      for (int i = 9; i < 18; ++i) row[i] = nan;
+    }
   }
 }
 

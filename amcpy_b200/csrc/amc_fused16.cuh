@@ -111,15 +111,6 @@ __global__ void init_twiddle16dif_kernel() {
 // conflict-free exchange layout for the 16 x 16 x R Stockham passes: low 4 bits ^= bits 4..7
 __device__ __forceinline__ int swz16(int e) { return e ^ ((e >> 4) & 15); }
 
-// Feature groups one instantiation of the kernel computes.  The C ABI's feature_mask picks the cheapest compiled
-// profile that covers the requested features (amc_api.cu: pick_profile); columns of groups that were not
-// computed are written as NaN.  kProfAll is the drop-in default (and the benchmarked kernel).
-constexpr int kProfFft = 1;     // feature 1            (spectral max: the three FFT stages)
-constexpr int kProfPhase = 2;   // features 2, 3, 5, 9  (atan2, wrapped differences, phase / frequency statistics)
-constexpr int kProfAmp = 4;     // features 4, 6, 7, 8  (|x| in FP64, centred amplitude sums)
-constexpr int kProfMom = 8;     // features 10..18      (the 15 monomial sums)
-constexpr int kProfAll = 15;
-
 constexpr int kTRow = 17;         // float2 per lane row of the warp-private exchange buffer (16 + 1 pad)
 constexpr int kPend16Stride = 25; // doubles per parked frame (25 totals; odd stride: conflict-free lane-per-frame reads)
 
@@ -250,16 +241,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         const int64_t fo = gg + static_cast<int64_t>(k - bi + lane) * tg;
         double* row = out + fo * out_stride;
         finalize_features(fs, N, row);
-        if constexpr (PROF != kProfAll) {              // groups this profile did not compute
-          const double nan = __longlong_as_double(0x7ff8000000000000LL);
-          if (!DO_FFT) row[0] = nan;
-          if (!DO_PHASE) row[1] = row[2] = row[4] = row[8] = nan;
-          if (!DO_AMP) row[3] = row[5] = row[6] = row[7] = nan;
-          if (!DO_MOM) {
-#pragma unroll
-            for (int i = 9; i < 18; ++i) row[i] = nan;
-          }
-        }
+        blank_skipped_groups<PROF>(row);
       }
       __syncwarp();
     }

@@ -30,12 +30,15 @@ struct FusedWCfg {
   static_assert(GROUP_BYTES % 16 == 0, "group region must keep 16-byte alignment");
 };
 
-template <int N, typename CT>
+template <int N, typename CT, int PROF = kProfAll>
 __global__ void __launch_bounds__(FusedWCfg<N, CT>::CTA, FusedWCfg<N, CT>::MIN_BLOCKS)
 fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame_stride,
                        double* __restrict__ out, int64_t out_stride) {
   using Cfg = FusedWCfg<N, CT>;
   constexpr int SPT = Cfg::SPT;
+  // feature groups of this instantiation (feature_mask profiles, see amc_device.cuh: kProf*)
+  constexpr bool DO_FFT = (PROF & kProfFft) != 0, DO_PHASE = (PROF & kProfPhase) != 0, DO_AMP = (PROF & kProfAmp) != 0,
+                 DO_MOM = (PROF & kProfMom) != 0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int g = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,15 +88,31 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
     for (int j = 0; j < SPT; ++j) {
       double a, b;
       load_sample<CT>(xs + lane + 32 * j, a, b, xr[j], xi[j]);
-      const double s = (j == 0) ? mono.init(a, b) : mono.add(a, b);
-      r[j] = sqrt_nr(s);
-      sum_r = (j == 0) ? r[j] : sum_r + r[j];
-      ph[j] = atan2_fast(xi[j], xr[j]);
+      double s = 0.0;
+      if constexpr (DO_MOM) {
+        s = (j == 0) ? mono.init(a, b) : mono.add(a, b);
+      } else {
+        if (j == 0) mono.clear();
+        if constexpr (DO_AMP) s = __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));   // as Monomials::add forms it
+      }
+      if constexpr (DO_AMP) {
+        r[j] = sqrt_nr(s);
+        sum_r = (j == 0) ? r[j] : sum_r + r[j];
+      } else {
+        r[j] = 0.0;
+        sum_r = 0.0;
+      }
+      if constexpr (DO_PHASE) ph[j] = atan2_fast(xi[j], xr[j]);
+      else ph[j] = 0.0f;
     }
     float fq[SPT];                                            // unwrapped phase steps in RADIANS (scaled when parked)
-    float s_ph = 0.0f, s_aph = 0.0f;
-    float tie_min = 1.0f;                                     // min | |dd| - pi | over this lane's steps
+    float s_ph = 0.0f, s_aph = 0.0f, s_f = 0.0f;
     const float last_keep = (lane == 31) ? 0.0f : 1.0f;       // sample N-1 has no successor
+    if constexpr (!DO_PHASE) {
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) fq[j] = 0.0f;
+    } else {
+    float tie_min = 1.0f;                                     // min | |dd| - pi | over this lane's steps
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
       // successor of (lane, j) is (lane+1, j); for lane 31 it is (0, j+1): lane 0 offers its next sample
@@ -121,9 +140,9 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
         for (int q = 0; q < SPT; ++q) fq[q] = (q == j) ? val : fq[q];
       }
     }
-    float s_f = 0.0f;
 #pragma unroll
     for (int j = 0; j < SPT; ++j) s_f += fq[j];
+    }   // DO_PHASE
 
     // 16 FP64 partials per lane -> lane l (and l + 16) holds the warp total of value l
     __syncwarp();                                             // the previous frame's column reads are done
@@ -157,30 +176,34 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
     float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
-      const double d = r[j] - mu_r;
-      const double d2 = d * d;
-      c2acc[0] += fabs(d);
-      c2acc[1] += d2;
-      c2acc[2] = fma(d2, d2, c2acc[2]);
-      const float e = ph[j] - mu_ph;
-      q2acc[0] = fmaf(e, e, q2acc[0]);
-      const float ea = fabsf(ph[j]) - mu_aph;
-      q2acc[1] = fmaf(ea, ea, q2acc[1]);
-      float ef = fq[j] - mu_f;
-      if (j == SPT - 1) ef *= last_keep;
-      const float ef2 = ef * ef;
-      q2acc[2] += ef2;
-      q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
+      if constexpr (DO_AMP) {
+        const double d = r[j] - mu_r;
+        const double d2 = d * d;
+        c2acc[0] += fabs(d);
+        c2acc[1] += d2;
+        c2acc[2] = fma(d2, d2, c2acc[2]);
+      }
+      if constexpr (DO_PHASE) {
+        const float e = ph[j] - mu_ph;
+        q2acc[0] = fmaf(e, e, q2acc[0]);
+        const float ea = fabsf(ph[j]) - mu_aph;
+        q2acc[1] = fmaf(ea, ea, q2acc[1]);
+        float ef = fq[j] - mu_f;
+        if (j == SPT - 1) ef *= last_keep;
+        const float ef2 = ef * ef;
+        q2acc[2] += ef2;
+        q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
+      }
     }
-    warp_sum_multi<double, 4>(c2acc, lane);                   // lane l: value l >> 3
-    warp_sum_multi<float, 4>(q2acc, lane);
+    if constexpr (DO_AMP) warp_sum_multi<double, 4>(c2acc, lane);   // lane l: value l >> 3
+    if constexpr (DO_PHASE) warp_sum_multi<float, 4>(q2acc, lane);
 
     // ---------------------------------------------------------------- FFT 8 x 8 x 4 through the slot
     __syncwarp();                                             // every lane has finished reading x
     float2* buf_a = reinterpret_cast<float2*>(slot_ptr);
     float2* buf_b = Cfg::C128 ? reinterpret_cast<float2*>(slot_ptr + N * 8) : fft_b_extra;
     float vmax = 0.0f;
-    {
+    if constexpr (DO_FFT) {
       // (the ~30 swizzled exchange indices are recomputed per frame from an opaque lane id: hoisted out of the
       // loop they were spilled and reloaded with LDL in front of every use)
       const int lf = opaque_if<true>(lane);
@@ -255,6 +278,7 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
         fs.spec_max = pl[24];
         const int64_t fo = gg + static_cast<int64_t>(it - bi + lane) * tg;
         finalize_features(fs, N, out + fo * out_stride);
+        blank_skipped_groups<PROF>(out + fo * out_stride);
       }
       __syncwarp();
     }

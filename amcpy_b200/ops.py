@@ -64,7 +64,7 @@ def extract_features(iq, out=None, stream=None, force_general: bool = False, fea
     """All 18 features of every frame of a device-resident complex tensor.
 
     feature_mask (default: all 18): the features the caller will read.  The library may skip the work of
-    feature groups outside the mask (FFT / phase+frequency / amplitude / moments; frame sizes 512..4096); the
+    feature groups outside the mask (FFT / phase+frequency / amplitude / moments; frame sizes 256..4096); the
     columns of a skipped group hold NaN, requested columns are bitwise what the full call returns.
 
     iq  : CUDA tensor (..., frame_size), complex128 or complex64 (north_star's batched entry takes

@@ -83,7 +83,7 @@ int amc_device_count(void);
  *                column holds the feature (bitwise the value an all-features call returns); an unwanted
  *                column holds either the feature or NaN - the library skips whole feature groups nobody
  *                asked for (FFT: 1; phase/frequency: 2,3,5,9; amplitude: 4,6,7,8; moments: 10..18) where a
- *                reduced kernel profile exists (frame sizes 512..4096).  AMC_ALL_FEATURES = the drop-in.
+ *                reduced kernel profile exists (frame sizes 256..4096).  AMC_ALL_FEATURES = the drop-in.
  * n_frames == 0 is a no-op.
  */
 int amc_extract_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size,

@@ -257,11 +257,11 @@ def test_run_extraction_fails_loudly_on_short_data(torch_cuda, tmp_path):
         run_extraction(cfg)
 
 
-@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096])
 @pytest.mark.parametrize("dtype", ["c128", "c64"])
 def test_feature_mask_profiles_skip_work_not_accuracy(torch_cuda, n, dtype):
     """feature_mask of the C ABI: requested columns are BITWISE what the all-features call returns, columns of
-    feature groups the library skipped hold NaN (frame sizes 512..4096 have reduced profiles: moments only,
+    feature groups the library skipped hold NaN (frame sizes 256..4096 have reduced profiles: moments only,
     amplitude + moments, everything but the FFT)."""
     from amcpy_b200 import ops
 
@@ -302,7 +302,7 @@ def test_feature_mask_is_ignored_where_no_reduced_profile_exists(torch_cuda):
     from amcpy_b200 import ops
 
     rng = np.random.default_rng(1)
-    for n in (100, 256, 8192):
+    for n in (100, 8192):
         x = torch_cuda.from_numpy(rng.standard_normal((5, n)) + 1j * rng.standard_normal((5, n))).cuda()
         full = ops.extract_features(x).cpu().numpy()
         got = ops.extract_features(x, feature_mask=ops.feature_mask_of([10, 11])).cpu().numpy()
