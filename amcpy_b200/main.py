@@ -41,7 +41,22 @@ def _config(args) -> Config:
     return Config(paths=Paths(root=args.root) if args.root else Paths(), signals=SignalConfig(**sig))
 
 
+def _init_distributed_if_launched() -> int:
+    """Under torchrun (WORLD_SIZE > 1) join the process group so that run_extraction's closing barrier works
+    (ranks take every world_size-th modulation on their own GPU).  Host-side rendezvous only: gloo."""
+    import os
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+
+        if dist.is_available() and not dist.is_initialized():
+            dist.init_process_group(backend="gloo")
+    return int(os.environ.get("RANK", "0"))
+
+
 def cmd_extract(cfg: Config, args=None) -> None:
+    _init_distributed_if_launched()
     run_extraction(cfg)
 
 
@@ -61,6 +76,8 @@ def cmd_full(cfg: Config, args=None) -> None:
     from .consumer import load_feature_set
 
     cmd_extract(cfg)
+    if _init_distributed_if_launched() != 0:
+        return                                   # the classifier is a single-GPU job: rank 0 trains
     x_train, x_test, y_train, y_test, scaler = load_feature_set(cfg, mode="training")
     print(f"feature set ready: train {tuple(x_train.shape)}, test {tuple(x_test.shape)}, "
           f"{len(set(y_train.tolist()))} classes")
@@ -75,7 +92,13 @@ def main(argv=None) -> None:
     args = _build_parser().parse_args(argv)
     cfg = _config(args)
     cfg.paths.ensure_dirs()
-    {"extract": cmd_extract, "full": cmd_full, "synth": cmd_synth}[args.command](cfg, args)
+    try:
+        {"extract": cmd_extract, "full": cmd_full, "synth": cmd_synth}[args.command](cfg, args)
+    finally:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
