@@ -23,6 +23,7 @@ AMC_C64, AMC_C128 = 0, 1
 AMC_FLAG_FORCE_GENERAL = 1
 AMC_FLAG_FUSED_SPT8 = 2
 AMC_FLAG_FUSED_WS = 4
+AMC_FLAG_DIRECT_DFT = 8
 AMC_ALL_FEATURES = 0x3FFFF
 
 NVCC_FLAGS = [

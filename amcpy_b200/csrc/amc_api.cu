@@ -2,10 +2,15 @@
 // and the chunked host-buffer pipeline.  No exceptions cross the boundary; no CPU compute path.
 #include "../../include/amcpy_b200.h"
 
+#include <cmath>
+#include <complex>
 #include <cstdarg>
 #include <cstdio>
+#include <map>
 #include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "amc_fused.cuh"
 #include "amc_fused16.cuh"
@@ -77,6 +82,88 @@ int ensure_twiddles(int dev, cudaStream_t stream) {
 }
 
 bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// Bluestein tables for frame sizes that are not powers of two (general kernel, fft_mode 2): built once per
+// (device, N) in float64 on the host - chirp c_n = exp(-i pi n^2 / N) and the length-M FFT of the wrapped
+// conjugate chirp, stored in the bit-reversed order the kernel's forward pass produces, scaled by 1/M -
+// and kept on the device.  The reference's np.fft.fft accepts any length (features.py:68).
+// ---------------------------------------------------------------------------------------------
+struct BluesteinTables {
+  float2* chirp = nullptr;   // N
+  float2* bfft = nullptr;    // M
+  int m = 0;
+};
+std::map<std::pair<int, int64_t>, BluesteinTables> g_bluestein;
+constexpr size_t kBluesteinMaxEntries = 64;          // beyond that many distinct sizes: direct DFT
+constexpr int64_t kBluesteinMinN = 128;              // below: the float64 direct DFT is cheap
+constexpr int64_t kBluesteinMaxM = 16384;            // M float2 of shared memory
+
+void host_fft_pow2(std::vector<std::complex<double>>& v) {
+  const size_t m = v.size();
+  for (size_t i = 1, j = 0; i < m; ++i) {            // bit-reversal permutation
+    size_t bit = m >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(v[i], v[j]);
+  }
+  const double pi = std::acos(-1.0);
+  for (size_t len = 2; len <= m; len <<= 1) {
+    for (size_t k = 0; k < len / 2; ++k) {
+      const std::complex<double> w = std::polar(1.0, -2.0 * pi * static_cast<double>(k) / static_cast<double>(len));
+      for (size_t i = k; i < m; i += len) {
+        const std::complex<double> u = v[i], t = w * v[i + len / 2];
+        v[i] = u + t;
+        v[i + len / 2] = u - t;
+      }
+    }
+  }
+}
+
+// returns AMC_OK with tab->m == 0 when this size should use the direct DFT instead
+int ensure_bluestein(int dev, int64_t n, cudaStream_t stream, BluesteinTables* tab) {
+  *tab = BluesteinTables();
+  if (n < kBluesteinMinN) return AMC_OK;
+  int64_t m = 1;
+  while (m < 2 * n - 1) m <<= 1;
+  if (m > kBluesteinMaxM) return AMC_OK;
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_bluestein.find({dev, n});
+  if (it != g_bluestein.end()) {
+    *tab = it->second;
+    return AMC_OK;
+  }
+  if (g_bluestein.size() >= kBluesteinMaxEntries) return AMC_OK;
+  const double pi = std::acos(-1.0);
+  std::vector<std::complex<double>> b(static_cast<size_t>(m));
+  std::vector<float2> chirp(static_cast<size_t>(n)), bf(static_cast<size_t>(m));
+  for (int64_t k = 0; k < n; ++k) {
+    const double ang = pi * static_cast<double>((k * k) % (2 * n)) / static_cast<double>(n);   // k^2 mod 2N: exact
+    const double cs = std::cos(ang), sn = std::sin(ang);
+    chirp[static_cast<size_t>(k)] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
+    b[static_cast<size_t>(k)] = {cs, sn};
+    if (k > 0) b[static_cast<size_t>(m - k)] = {cs, sn};
+  }
+  host_fft_pow2(b);
+  int bits = 0;
+  while ((int64_t{1} << bits) < m) ++bits;
+  for (int64_t j = 0; j < m; ++j) {
+    int64_t r = 0;
+    for (int q = 0; q < bits; ++q) r |= ((j >> q) & 1) << (bits - 1 - q);
+    const std::complex<double> v = b[static_cast<size_t>(r)] / static_cast<double>(m);
+    bf[static_cast<size_t>(j)] = make_float2(static_cast<float>(v.real()), static_cast<float>(v.imag()));
+  }
+  BluesteinTables t;
+  t.m = static_cast<int>(m);
+  AMC_CUDA(cudaMalloc(&t.chirp, static_cast<size_t>(n) * sizeof(float2)));
+  AMC_CUDA(cudaMalloc(&t.bfft, static_cast<size_t>(m) * sizeof(float2)));
+  AMC_CUDA(cudaMemcpyAsync(t.chirp, chirp.data(), static_cast<size_t>(n) * sizeof(float2), cudaMemcpyHostToDevice, stream));
+  AMC_CUDA(cudaMemcpyAsync(t.bfft, bf.data(), static_cast<size_t>(m) * sizeof(float2), cudaMemcpyHostToDevice, stream));
+  AMC_CUDA(cudaStreamSynchronize(stream));   // once per (device, N): later calls on other streams rely on it
+  g_bluestein[{dev, n}] = t;
+  *tab = t;
+  return AMC_OK;
+}
 
 template <int N, typename CT>
 int launch_fused(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride,
@@ -274,9 +361,10 @@ constexpr int64_t kGeneralDftMax = 12288;    // N double2 of twiddles must fit i
 
 template <typename CT>
 int launch_general(const void* iq, int64_t n_frames, int64_t n, int64_t frame_stride, int64_t sample_stride,
-                   double* out, int64_t out_stride, int sms, cudaStream_t stream) {
+                   double* out, int64_t out_stride, int sms, cudaStream_t stream, int flags) {
   int fft_mode;
   size_t dyn;
+  BluesteinTables bl;
   if (is_pow2(n) && n >= 2) {
     if (n > kGeneralPow2Max)
       return fail(AMC_ERR_UNSUPPORTED, "power-of-two frame_size %lld > %lld not supported", (long long)n,
@@ -287,15 +375,25 @@ int launch_general(const void* iq, int64_t n_frames, int64_t n, int64_t frame_st
     if (n > kGeneralDftMax)
       return fail(AMC_ERR_UNSUPPORTED, "non-power-of-two frame_size %lld > %lld not supported", (long long)n,
                   (long long)kGeneralDftMax);
-    fft_mode = 0;
-    dyn = static_cast<size_t>(n) * sizeof(double2);
+    int dev = 0;
+    AMC_CUDA(cudaGetDevice(&dev));
+    const int rc = (flags & AMC_FLAG_DIRECT_DFT) ? AMC_OK : ensure_bluestein(dev, n, stream, &bl);
+    if (rc != AMC_OK) return rc;
+    if (bl.m > 0) {
+      fft_mode = 2;
+      dyn = static_cast<size_t>(bl.m) * sizeof(float2);
+    } else {
+      fft_mode = 0;
+      dyn = static_cast<size_t>(n) * sizeof(double2);
+    }
   }
   auto kern = amc::general_features_kernel<CT>;
   AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int64_t cap = static_cast<int64_t>(sms) * 4;
   const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
   kern<<<grid, amc::kGenThreads, dyn, stream>>>(static_cast<const CT*>(iq), n_frames, static_cast<int>(n),
-                                               frame_stride, sample_stride, out, out_stride, fft_mode);
+                                               frame_stride, sample_stride, out, out_stride, fft_mode, bl.chirp,
+                                               bl.bfft, bl.m);
   ++t_launches;
   AMC_CUDA(cudaGetLastError());
   return AMC_OK;
@@ -405,9 +503,9 @@ int amc_extract_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t fr
   }
   if (iq_dtype == AMC_C128)
     return launch_general<double2>(iq, n_frames, frame_size, frame_stride, sample_stride, out, out_stride, di.sms,
-                                   stream);
+                                   stream, flags);
   return launch_general<float2>(iq, n_frames, frame_size, frame_stride, sample_stride, out, out_stride, di.sms,
-                                stream);
+                                stream, flags);
 }
 
 int amc_frames_from_sample_major(const void* src, int iq_dtype, int64_t n_frames, int64_t frame_size,

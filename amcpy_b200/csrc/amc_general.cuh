@@ -54,12 +54,54 @@ __device__ __forceinline__ double block_max(double x, double* red, int tid) {
   return m;
 }
 
+// In-place radix-2 FFT passes over `m` float2 in shared memory (m a power of two, every thread of the CTA calls).
+// Forward: decimation in frequency, natural order in -> bit-reversed order out.
+__device__ __forceinline__ void smem_fft_dif(float2* buf, int m, int tid) {
+  for (int half = m >> 1; half >= 1; half >>= 1) {
+    const float inv_half = 1.0f / static_cast<float>(half);
+    for (int p = tid; p < (m >> 1); p += kGenThreads) {
+      const int off = p & (half - 1);
+      const int i0 = ((p - off) << 1) + off;
+      const float2 u = buf[i0], w = buf[i0 + half];
+      buf[i0] = make_float2(u.x + w.x, u.y + w.y);
+      const float dx = u.x - w.x, dy = u.y - w.y;
+      float sn, cs;
+      sincospif(-static_cast<float>(off) * inv_half, &sn, &cs);
+      buf[i0 + half] = make_float2(dx * cs - dy * sn, dx * sn + dy * cs);
+    }
+    __syncthreads();
+  }
+}
+// Inverse (unscaled: m * IDFT): decimation in time with conjugate twiddles, bit-reversed order in -> natural order
+// out - the stages of smem_fft_dif undone in reverse order.
+__device__ __forceinline__ void smem_ifft_dit(float2* buf, int m, int tid) {
+  for (int half = 1; half < m; half <<= 1) {
+    const float inv_half = 1.0f / static_cast<float>(half);
+    for (int p = tid; p < (m >> 1); p += kGenThreads) {
+      const int off = p & (half - 1);
+      const int i0 = ((p - off) << 1) + off;
+      const float2 u = buf[i0], w = buf[i0 + half];
+      float sn, cs;
+      sincospif(static_cast<float>(off) * inv_half, &sn, &cs);
+      const float tx = w.x * cs - w.y * sn, ty = w.x * sn + w.y * cs;
+      buf[i0] = make_float2(u.x + tx, u.y + ty);
+      buf[i0 + half] = make_float2(u.x - tx, u.y - ty);
+    }
+    __syncthreads();
+  }
+}
+
 // fft_mode: 0 = direct DFT (float64, twiddle table of N double2 in dynamic smem),
-//           1 = power-of-two in-place radix-2 DIF (float32, N float2 in dynamic smem)
+//           1 = power-of-two in-place radix-2 DIF (float32, N float2 in dynamic smem),
+//           2 = Bluestein (chirp-z) for other lengths: x_n c_n (c_n = exp(-i pi n^2 / N)) zero-padded to bl_m =
+//               pow2 >= 2N-1, FFT, times the pre-transformed conjugate chirp `bl_bfft` (bit-reversed order, 1/bl_m
+//               folded in), inverse FFT; |X_k| = |conv_k| for k < N, so the closing chirp multiply is not needed for
+//               the spectral max (float32, bl_m float2 in dynamic smem; tables built once per N by the host side)
 template <typename CT>
 __global__ void __launch_bounds__(kGenThreads)
 general_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int64_t frame_stride,
-                        int64_t sample_stride, double* __restrict__ out, int64_t out_stride, int fft_mode) {
+                        int64_t sample_stride, double* __restrict__ out, int64_t out_stride, int fft_mode,
+                        const float2* __restrict__ bl_chirp, const float2* __restrict__ bl_bfft, int bl_m) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ double red[kGenWarps * 20];
   const int tid = threadIdx.x;
@@ -142,20 +184,33 @@ general_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int6
         buf[i] = make_float2(static_cast<float>(a), static_cast<float>(b));
       }
       __syncthreads();
-      for (int half = n >> 1; half >= 1; half >>= 1) {
-        const float inv_half = 1.0f / static_cast<float>(half);
-        for (int p = tid; p < (n >> 1); p += kGenThreads) {
-          const int off = p & (half - 1);
-          const int i0 = ((p - off) << 1) + off;
-          const float2 u = buf[i0], w = buf[i0 + half];
-          buf[i0] = make_float2(u.x + w.x, u.y + w.y);
-          const float dx = u.x - w.x, dy = u.y - w.y;
-          float sn, cs;
-          sincospif(-static_cast<float>(off) * inv_half, &sn, &cs);
-          buf[i0 + half] = make_float2(dx * cs - dy * sn, dx * sn + dy * cs);
-        }
-        __syncthreads();
+      smem_fft_dif(buf, n, tid);
+      for (int i = tid; i < n; i += kGenThreads) {
+        const float2 u = buf[i];
+        smax = fmax(smax, static_cast<double>(u.x) * u.x + static_cast<double>(u.y) * u.y);
       }
+      __syncthreads();
+    } else if (fft_mode == 2) {
+      float2* buf = reinterpret_cast<float2*>(dyn);
+      for (int i = tid; i < bl_m; i += kGenThreads) {
+        float2 v = make_float2(0.0f, 0.0f);
+        if (i < n) {
+          double a, b;
+          load_strided(base, i, sample_stride, a, b);
+          const float2 c = bl_chirp[i];
+          const float af = static_cast<float>(a), bf = static_cast<float>(b);
+          v = make_float2(af * c.x - bf * c.y, af * c.y + bf * c.x);
+        }
+        buf[i] = v;
+      }
+      __syncthreads();
+      smem_fft_dif(buf, bl_m, tid);
+      for (int i = tid; i < bl_m; i += kGenThreads) {
+        const float2 u = buf[i], w = bl_bfft[i];
+        buf[i] = make_float2(u.x * w.x - u.y * w.y, u.x * w.y + u.y * w.x);
+      }
+      __syncthreads();
+      smem_ifft_dit(buf, bl_m, tid);
       for (int i = tid; i < n; i += kGenThreads) {
         const float2 u = buf[i];
         smax = fmax(smax, static_cast<double>(u.x) * u.x + static_cast<double>(u.y) * u.y);

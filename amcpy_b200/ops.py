@@ -60,7 +60,7 @@ def feature_mask_of(feature_ids) -> int:
 
 
 def extract_features(iq, out=None, stream=None, force_general: bool = False, feature_mask: int = nat.AMC_ALL_FEATURES,
-                     spt8: bool = False, ws: bool = False):
+                     spt8: bool = False, ws: bool = False, direct_dft: bool = False):
     """All 18 features of every frame of a device-resident complex tensor.
 
     feature_mask (default: all 18): the features the caller will read.  The library may skip the work of
@@ -72,6 +72,8 @@ def extract_features(iq, out=None, stream=None, force_general: bool = False, fea
     out : optional CUDA float64 tensor (..., 18), C-contiguous.
     spt8: A/B switch - run the first-generation 8-samples-per-thread fused kernel.
     ws  : A/B switch - run the warp-specialised (FP64 warps / FP32 warps) variant, N = 2048 only.
+    direct_dft: cross-check switch - frame sizes that are not powers of two use the float64 direct DFT (O(N^2))
+          instead of the float32 Bluestein FFT of the general kernel.
     Returns float64 (..., 18); column k = feature id k+1.  Enqueued on `stream`
     (default: torch's current stream); does not synchronise.
     """
@@ -89,7 +91,7 @@ def extract_features(iq, out=None, stream=None, force_general: bool = False, fea
             x.data_ptr(), _dtype_code(x), n_frames, n, x.stride(0) if n_frames > 1 else n, x.stride(1) if n > 1 else 1,
             out.data_ptr(), N_FEATURES, feature_mask,
             (nat.AMC_FLAG_FORCE_GENERAL if force_general else 0) | (nat.AMC_FLAG_FUSED_SPT8 if spt8 else 0)
-            | (nat.AMC_FLAG_FUSED_WS if ws else 0),
+            | (nat.AMC_FLAG_FUSED_WS if ws else 0) | (nat.AMC_FLAG_DIRECT_DFT if direct_dft else 0),
             _stream_ptr(stream),
         )
     nat.check(rc)

@@ -33,7 +33,10 @@
  *   relative 1e-9 : features 4, 6, 7, 8 and 10..18 (float64 accumulation)
  *   relative 1e-6 : features 1, 2, 3, 5, 9 (float32 FFT / atan2 in the fused kernel; unwrap branch
  *                   decisions within 4e-6 rad of +-pi are re-decided in float64 exactly as np.unwrap)
- *   AMC_FLAG_FORCE_GENERAL computes everything except the power-of-two FFT in float64.
+ *   AMC_FLAG_FORCE_GENERAL computes everything except the FFT in float64.
+ * General-kernel spectrum: power-of-two sizes <= 16384 by a float32 radix-2 FFT; other sizes from 128 to 8192 by a
+ * float32 Bluestein (chirp-z) FFT; smaller sizes and 8193..12288 by a float64 direct DFT; anything larger returns
+ * AMC_ERR_UNSUPPORTED.
  */
 #ifndef AMCPY_B200_H
 #define AMCPY_B200_H
@@ -56,6 +59,7 @@ extern "C" {
 #define AMC_FLAG_FORCE_GENERAL 1 /* never take the fused fixed-size kernel */
 #define AMC_FLAG_FUSED_SPT8 2     /* fused kernel variant with 8 samples per thread (kept for N=256 and for A/B runs) */
 #define AMC_FLAG_FUSED_WS 4       /* N = 2048 only: warp-specialised variant (FP64 warps / FP32 warps), A/B runs */
+#define AMC_FLAG_DIRECT_DFT 8     /* non-power-of-two sizes: float64 direct DFT instead of the float32 Bluestein FFT (cross-check) */
 
 /* return codes */
 #define AMC_OK 0
@@ -76,7 +80,9 @@ int amc_device_count(void);
 /*
  * All 18 features of n_frames frames that already live in device memory (current device),
  * enqueued on `cuda_stream` (a cudaStream_t, may be NULL for the default stream); does not
- * synchronise, does not allocate.
+ * synchronise, does not allocate - except that the FIRST call on a device (twiddle tables) and the first
+ * call for a new non-power-of-two frame size (Bluestein tables, <= 192 KB, cached per device and size)
+ * build their tables and wait for that once.
  *   iq           device pointer, complex64/complex128 interleaved
  *   out          device pointer, float64, row f at out + f*out_stride, out_stride >= 18
  *   feature_mask bit k = feature k+1 wanted; must be non-zero.  All 18 columns are always written: a wanted

@@ -66,6 +66,33 @@ def test_ragged_and_large_frame_sizes(torch_cuda, n):
     assert_features_close(got, want)
 
 
+@pytest.mark.parametrize("n", [127, 128, 129, 255, 257, 1000, 1023, 1025, 1536, 2047, 3000, 4097, 6000, 8191, 8193])
+def test_non_power_of_two_sizes_bluestein_vs_oracle_and_direct_dft(torch_cuda, n):
+    """np.fft.fft takes any length (features.py:68): sizes 128..8192 that are not powers of two run a float32
+    Bluestein FFT in the general kernel (127 and 8193 the float64 direct DFT).  Both must match the oracle;
+    everything but feature 1 must be bitwise the same in the two modes."""
+    from amcpy_b200 import ops, synth
+    from oracle import amc_oracle as orc
+
+    x = np.concatenate([synth.cell(m, snr, 3, range(2), n, seed=n) for m, snr in ((0, 18.0), (3, 4.0), (5, -6.0))])
+    x[1] *= 37.5                                           # scale must not matter
+    x[2] += 0.3 - 0.2j                                     # a DC line: one dominant bin
+    x[3] *= np.exp(2j * np.pi * 0.123 * np.arange(n))      # carrier offset: the peak moves between bins
+    want = orc.features_batch(x)
+    xd = torch_cuda.from_numpy(x).cuda()
+    got = ops.extract_features(xd).cpu().numpy()
+    ref = ops.extract_features(xd, direct_dft=True).cpu().numpy()
+    assert_features_close(got, want)
+    assert_features_close(ref, want)
+    assert np.array_equal(got[:, 1:], ref[:, 1:])
+    rel = np.max(np.abs(got[:, 0] - ref[:, 0]) / ref[:, 0])
+    assert rel < 1e-6, f"N={n}: Bluestein vs float64 DFT {rel:.2e}"
+    # complex64 input takes the same route
+    g32 = ops.extract_features(torch_cuda.from_numpy(x.astype(np.complex64)).cuda()).cpu().numpy()
+    w32 = orc.features_batch(x.astype(np.complex64).astype(np.complex128))
+    assert_features_close(g32, w32)
+
+
 @pytest.mark.parametrize("n", [256, 1024, 2048, 4096])
 def test_first_generation_fused_kernel_still_in_parity(torch_cuda, n):
     # AMC_FLAG_FUSED_SPT8: the 8-samples-per-thread kernel kept for A/B runs
