@@ -387,13 +387,24 @@ int launch_general(const void* iq, int64_t n_frames, int64_t n, int64_t frame_st
       dyn = static_cast<size_t>(n) * sizeof(double2);
     }
   }
+  // phase / amplitude cache of 2 N doubles between the passes: aliases the FFT buffer (modes 1, 2) or follows the
+  // DFT twiddle table (mode 0); skipped when it does not fit
+  int cache_off = -1;
+  {
+    const size_t cache = static_cast<size_t>(n) * 2 * sizeof(double);
+    const size_t off = fft_mode == 0 ? dyn : 0;
+    if (off + cache <= 200 * 1024) {
+      cache_off = static_cast<int>(off);
+      if (off + cache > dyn) dyn = off + cache;
+    }
+  }
   auto kern = amc::general_features_kernel<CT>;
   AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int64_t cap = static_cast<int64_t>(sms) * 4;
   const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
   kern<<<grid, amc::kGenThreads, dyn, stream>>>(static_cast<const CT*>(iq), n_frames, static_cast<int>(n),
                                                frame_stride, sample_stride, out, out_stride, fft_mode, bl.chirp,
-                                               bl.bfft, bl.m);
+                                               bl.bfft, bl.m, cache_off);
   ++t_launches;
   AMC_CUDA(cudaGetLastError());
   return AMC_OK;

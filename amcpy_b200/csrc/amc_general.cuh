@@ -97,11 +97,16 @@ __device__ __forceinline__ void smem_ifft_dit(float2* buf, int m, int tid) {
 //               pow2 >= 2N-1, FFT, times the pre-transformed conjugate chirp `bl_bfft` (bit-reversed order, 1/bl_m
 //               folded in), inverse FFT; |X_k| = |conv_k| for k < N, so the closing chirp multiply is not needed for
 //               the spectral max (float32, bl_m float2 in dynamic smem; tables built once per N by the host side)
+// cache_off >= 0: byte offset in dynamic smem of 2 N doubles that keep every sample's phase and amplitude between the
+//           passes (one libdevice atan2 + one hypot per sample instead of four + two; same values, same summation
+//           order, so the results do not depend on it); it may alias the FFT buffer, which is only used afterwards.
+//           -1 when it does not fit (N > 12800): the values are recomputed.
 template <typename CT>
 __global__ void __launch_bounds__(kGenThreads)
 general_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int64_t frame_stride,
                         int64_t sample_stride, double* __restrict__ out, int64_t out_stride, int fft_mode,
-                        const float2* __restrict__ bl_chirp, const float2* __restrict__ bl_bfft, int bl_m) {
+                        const float2* __restrict__ bl_chirp, const float2* __restrict__ bl_bfft, int bl_m,
+                        int cache_off) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ double red[kGenWarps * 20];
   const int tid = threadIdx.x;
@@ -116,6 +121,10 @@ general_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int6
     __syncthreads();
   }
 
+  const bool cached = cache_off >= 0;
+  double* ph_c = reinterpret_cast<double*>(dyn + (cached ? cache_off : 0));
+  double* r_c = ph_c + n;
+
   for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
     const CT* base = iq + f * frame_stride;
 
@@ -127,15 +136,23 @@ general_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int6
       double a, b;
       load_strided(base, i, sample_stride, a, b);
       mono.add(a, b);
-      sr += hypot(a, b);                              // np.abs == hypot (features.py:27)
+      const double r0 = hypot(a, b);                  // np.abs == hypot (features.py:27)
+      sr += r0;
       const double p0 = atan2_exact(b, a);            // np.angle  (features.py:28)
       sph += p0;
       saph += fabs(p0);
-      if (i + 1 < n) {
+      if (cached) {
+        ph_c[i] = p0;
+        r_c[i] = r0;
+      } else if (i + 1 < n) {
         double a1, b1;
         load_strided(base, i + 1, sample_stride, a1, b1);
         sfq += unwrap_step(atan2_exact(b1, a1) - p0) / kTwoPi;   // features.py:29-30
       }
+    }
+    if (cached) {
+      __syncthreads();
+      for (int i = tid; i + 1 < n; i += kGenThreads) sfq += unwrap_step(ph_c[i + 1] - ph_c[i]) / kTwoPi;
     }
     double v1[19];
 #pragma unroll
@@ -152,21 +169,32 @@ general_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int6
     // ---- pass 2: centred sums ---------------------------------------------------------
     double v2[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int i = tid; i < n; i += kGenThreads) {
-      double a, b;
-      load_strided(base, i, sample_stride, a, b);
-      const double d = hypot(a, b) - mu_r;
+      double r0, p0, p1 = 0.0;
+      if (cached) {
+        r0 = r_c[i];
+        p0 = ph_c[i];
+        if (i + 1 < n) p1 = ph_c[i + 1];
+      } else {
+        double a, b;
+        load_strided(base, i, sample_stride, a, b);
+        r0 = hypot(a, b);
+        p0 = atan2_exact(b, a);
+        if (i + 1 < n) {
+          double a1, b1;
+          load_strided(base, i + 1, sample_stride, a1, b1);
+          p1 = atan2_exact(b1, a1);
+        }
+      }
+      const double d = r0 - mu_r;
       const double d2 = d * d;
       v2[0] += fabs(d);
       v2[1] += d2;
       v2[2] += d2 * d2;
-      const double p0 = atan2_exact(b, a);
       const double e = p0 - mu_ph, ea = fabs(p0) - mu_aph;
       v2[3] += e * e;
       v2[4] += ea * ea;
       if (i + 1 < n) {
-        double a1, b1;
-        load_strided(base, i + 1, sample_stride, a1, b1);
-        const double ef = unwrap_step(atan2_exact(b1, a1) - p0) / kTwoPi - mu_f;
+        const double ef = unwrap_step(p1 - p0) / kTwoPi - mu_f;
         const double ef2 = ef * ef;
         v2[5] += ef2;
         v2[6] += ef2 * ef2;
