@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <map>
 #include <mutex>
+#include <cstring>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -430,6 +432,11 @@ struct HostPipe {
   void* d_tr[2] = {nullptr, nullptr};   // transposed copy for sample-major input
   double* d_out[2] = {nullptr, nullptr};
   size_t in_bytes = 0, tr_bytes = 0, out_bytes = 0;
+  // pageable sources (numpy arrays, memory-mapped .mat planes): gathered by a few host threads into these pinned
+  // buffers and copied from there - a cudaMemcpy2DAsync from pageable memory is staged by the driver on ONE thread
+  void* h_in[2] = {nullptr, nullptr};
+  cudaEvent_t h2d_done[2] = {nullptr, nullptr};
+  size_t h_bytes = 0;
 };
 HostPipe g_pipe[kMaxDevices];
 std::mutex g_pipe_mu[kMaxDevices];
@@ -460,6 +467,84 @@ int ensure_pipe(HostPipe& p, size_t in_bytes, size_t tr_bytes, size_t out_bytes)
   if (p.tr_bytes < tr_bytes) p.tr_bytes = tr_bytes;
   if (p.out_bytes < out_bytes) p.out_bytes = out_bytes;
   return AMC_OK;
+}
+
+int ensure_pinned_staging(HostPipe& p, size_t bytes) {
+  for (int i = 0; i < 2; ++i) {
+    if (!p.h2d_done[i]) AMC_CUDA(cudaEventCreateWithFlags(&p.h2d_done[i], cudaEventDisableTiming));
+    if (p.h_bytes < bytes) {
+      if (p.h_in[i]) AMC_CUDA(cudaFreeHost(p.h_in[i]));
+      p.h_in[i] = nullptr;
+      AMC_CUDA(cudaMallocHost(&p.h_in[i], bytes));
+    }
+  }
+  if (p.h_bytes < bytes) p.h_bytes = bytes;
+  return AMC_OK;
+}
+
+// true for ordinary (pageable, unregistered) host memory; pinned / registered / managed memory is copied directly
+bool is_pageable_host(const void* ptr) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+    cudaGetLastError();   // older runtimes report unregistered host memory as an error: clear it
+    return true;
+  }
+  return attr.type == cudaMemoryTypeUnregistered;
+}
+
+int host_copy_threads() {
+  static const int n = [] {
+    const char* env = std::getenv("AMCPY_B200_COPY_THREADS");
+    if (env && *env) {
+      const int v = std::atoi(env);
+      if (v >= 1) return v > 64 ? 64 : v;
+    }
+    const unsigned hc = std::thread::hardware_concurrency();
+    const int v = hc >= 16 ? 8 : (hc >= 4 ? static_cast<int>(hc / 2) : 1);
+    return v;
+  }();
+  return n;
+}
+
+// dst[r * dst_pitch .. + row_bytes) = src[r * src_pitch .. + row_bytes) for r < n_rows, rows spread over host threads
+void gather_rows(unsigned char* dst, size_t dst_pitch, const unsigned char* src, size_t src_pitch, size_t row_bytes,
+                 size_t n_rows) {
+  const size_t total = row_bytes * n_rows;
+  int nt = host_copy_threads();
+  if (total < (4u << 20) || nt <= 1) nt = 1;
+  auto work = [=](size_t r0, size_t r1) {
+    if (dst_pitch == row_bytes && src_pitch == row_bytes) {
+      std::memcpy(dst + r0 * row_bytes, src + r0 * row_bytes, (r1 - r0) * row_bytes);
+    } else {
+      for (size_t r = r0; r < r1; ++r) std::memcpy(dst + r * dst_pitch, src + r * src_pitch, row_bytes);
+    }
+  };
+  if (nt == 1) {
+    work(0, n_rows);
+    return;
+  }
+  if (n_rows < static_cast<size_t>(nt)) {   // few long rows (one contiguous block): split by bytes instead
+    if (n_rows == 1 || (dst_pitch == row_bytes && src_pitch == row_bytes)) {
+      const size_t per = (total + nt - 1) / nt;
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; ++t) {
+        const size_t b0 = per * t, b1 = (b0 + per < total) ? b0 + per : total;
+        if (b0 >= b1) break;
+        th.emplace_back([=] { std::memcpy(dst + b0, src + b0, b1 - b0); });
+      }
+      for (auto& t : th) t.join();
+      return;
+    }
+    nt = static_cast<int>(n_rows);
+  }
+  std::vector<std::thread> th;
+  const size_t per = (n_rows + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    const size_t r0 = per * t, r1 = (r0 + per < n_rows) ? r0 + per : n_rows;
+    if (r0 >= r1) break;
+    th.emplace_back(work, r0, r1);
+  }
+  for (auto& t : th) t.join();
 }
 
 }  // namespace
@@ -651,6 +736,14 @@ int amc_extract_host(const void* iq, int iq_dtype, int64_t n_frames, int64_t fra
     return rc;
   }
   const unsigned char* src = static_cast<const unsigned char*>(iq);
+  const bool staged = is_pageable_host(iq) && static_cast<size_t>(n_frames) * frame_bytes >= (8u << 20);
+  if (staged) {
+    rc = ensure_pinned_staging(p, static_cast<size_t>(chunk) * frame_bytes);
+    if (rc != AMC_OK) {
+      cudaSetDevice(prev);
+      return rc;
+    }
+  }
   int status = AMC_OK;
   int64_t c = 0;
   for (int64_t f0 = 0; f0 < n_frames && status == AMC_OK; f0 += chunk, ++c) {
@@ -659,7 +752,21 @@ int amc_extract_host(const void* iq, int iq_dtype, int64_t n_frames, int64_t fra
     cudaStream_t st = p.stream[b];
     cudaError_t e;
     const void* dev_frames = p.d_in[b];
-    if (row_major && (frame_stride == frame_size || nf == 1)) {   // contiguous rows: one linear copy
+    if (staged) {   // host threads gather the chunk into pinned memory (same layout as the device buffer), one linear copy
+      e = c >= 2 ? cudaEventSynchronize(p.h2d_done[b]) : cudaSuccess;   // the copy that last read this buffer is done
+      if (e == cudaSuccess) {
+        unsigned char* h = static_cast<unsigned char*>(p.h_in[b]);
+        if (row_major)
+          gather_rows(h, frame_bytes, src + static_cast<size_t>(f0) * frame_stride * elt,
+                      (nf == 1 ? frame_bytes : static_cast<size_t>(frame_stride) * elt), frame_bytes, static_cast<size_t>(nf));
+        else
+          gather_rows(h, static_cast<size_t>(nf) * elt, src + static_cast<size_t>(f0) * elt,
+                      static_cast<size_t>(sample_stride) * elt, static_cast<size_t>(nf) * elt,
+                      static_cast<size_t>(frame_size));
+        e = cudaMemcpyAsync(p.d_in[b], h, static_cast<size_t>(nf) * frame_bytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(p.h2d_done[b], st);
+      }
+    } else if (row_major && (frame_stride == frame_size || nf == 1)) {   // contiguous rows: one linear copy
       e = cudaMemcpyAsync(p.d_in[b], src + static_cast<size_t>(f0) * frame_stride * elt,
                           static_cast<size_t>(nf) * frame_bytes, cudaMemcpyHostToDevice, st);
     } else if (row_major) {
@@ -733,6 +840,14 @@ int amc_extract_host_planar(const void* re, const void* im, int iq_dtype, int64_
   }
   const unsigned char* src_re = static_cast<const unsigned char*>(re);
   const unsigned char* src_im = static_cast<const unsigned char*>(im);
+  const bool staged = is_pageable_host(re) && static_cast<size_t>(n_frames) * frame_bytes >= (8u << 20);
+  if (staged) {
+    rc = ensure_pinned_staging(p, static_cast<size_t>(chunk) * frame_bytes);
+    if (rc != AMC_OK) {
+      cudaSetDevice(prev);
+      return rc;
+    }
+  }
   int status = AMC_OK;
   int64_t c = 0;
   for (int64_t f0 = 0; f0 < n_frames && status == AMC_OK; f0 += chunk, ++c) {
@@ -742,11 +857,25 @@ int amc_extract_host_planar(const void* re, const void* im, int iq_dtype, int64_
     unsigned char* d_re = static_cast<unsigned char*>(p.d_in[b]);
     unsigned char* d_im = d_re + static_cast<size_t>(nf) * frame_size * relt;   // second half of the staging buffer
     const size_t row = static_cast<size_t>(nf) * relt, pitch = static_cast<size_t>(sample_stride) * relt;
-    cudaError_t e = cudaMemcpy2DAsync(d_re, row, src_re + static_cast<size_t>(f0) * relt, pitch, row,
-                                      static_cast<size_t>(frame_size), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && src_im)
-      e = cudaMemcpy2DAsync(d_im, row, src_im + static_cast<size_t>(f0) * relt, pitch, row,
+    cudaError_t e;
+    if (staged) {   // host threads gather both planes of the chunk into pinned memory, one linear copy
+      e = c >= 2 ? cudaEventSynchronize(p.h2d_done[b]) : cudaSuccess;
+      if (e == cudaSuccess) {
+        unsigned char* h = static_cast<unsigned char*>(p.h_in[b]);
+        const size_t plane = row * static_cast<size_t>(frame_size);
+        gather_rows(h, row, src_re + static_cast<size_t>(f0) * relt, pitch, row, static_cast<size_t>(frame_size));
+        if (src_im)
+          gather_rows(h + plane, row, src_im + static_cast<size_t>(f0) * relt, pitch, row, static_cast<size_t>(frame_size));
+        e = cudaMemcpyAsync(d_re, h, src_im ? 2 * plane : plane, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(p.h2d_done[b], st);
+      }
+    } else {
+      e = cudaMemcpy2DAsync(d_re, row, src_re + static_cast<size_t>(f0) * relt, pitch, row,
                             static_cast<size_t>(frame_size), cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess && src_im)
+        e = cudaMemcpy2DAsync(d_im, row, src_im + static_cast<size_t>(f0) * relt, pitch, row,
+                              static_cast<size_t>(frame_size), cudaMemcpyHostToDevice, st);
+    }
     if (e != cudaSuccess) {
       status = fail(AMC_ERR_CUDA, "host->device copy failed: %s", cudaGetErrorString(e));
       break;

@@ -149,6 +149,25 @@ def test_host_pipeline_row_major_and_sample_major(torch_cuda):
         np.ascontiguousarray(flat[:, :1000])), scale=1e-3)  # padded rows through the general kernel
 
 
+def test_host_pipeline_pageable_sources_are_staged_through_pinned_memory(torch_cuda):
+    """Pageable host sources >= 8 MB (numpy arrays, memory-mapped files) are gathered by host threads into the
+    library's pinned staging buffers; pinned sources are copied directly.  Same frames, same kernel: bitwise equal,
+    for contiguous rows, padded rows and the sample-major layout."""
+    from amcpy_b200 import ops
+
+    x, _ = golden_frames(2048)
+    big = np.concatenate([x.reshape(-1, 2048)] * 40)        # 94 MB pageable: two chunks
+    pinned = torch_cuda.from_numpy(big).pin_memory()
+    direct = ops.extract_features_host(pinned.numpy())      # pinned: no staging
+    assert np.array_equal(ops.extract_features_host(big), direct)
+    assert np.array_equal(ops.extract_features_host(np.asfortranarray(big)), direct)
+    view = big[:, :1024]                                    # padded rows (stride 2048), 47 MB of payload
+    assert np.array_equal(ops.extract_features_host(view), ops.extract_features(torch_cuda.from_numpy(
+        np.ascontiguousarray(view)).cuda()).cpu().numpy())
+    one = big[:1]                                           # a single frame stays on the direct path
+    assert np.array_equal(ops.extract_features_host(one), direct[:1])
+
+
 def test_host_pipeline_planar_planes_match_interleaved(torch_cuda):
     """amc_extract_host_planar (split real / imaginary sample-major planes, as memory-mapped from a .mat file)
     feeds the same kernel the same frames as the interleaved host path: bitwise equal results."""
