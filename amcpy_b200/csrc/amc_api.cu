@@ -137,8 +137,15 @@ int ensure_bluestein(int dev, int64_t n, cudaStream_t stream, BluesteinTables* t
   }
   if (g_bluestein.size() >= kBluesteinMaxEntries) return AMC_OK;
   const double pi = std::acos(-1.0);
-  std::vector<std::complex<double>> b(static_cast<size_t>(m));
-  std::vector<float2> chirp(static_cast<size_t>(n)), bf(static_cast<size_t>(m));
+  std::vector<std::complex<double>> b;
+  std::vector<float2> chirp, bf;
+  try {
+    b.resize(static_cast<size_t>(m));
+    chirp.resize(static_cast<size_t>(n));
+    bf.resize(static_cast<size_t>(m));
+  } catch (...) {
+    return AMC_OK;   // no host memory for the tables: the direct DFT needs none
+  }
   for (int64_t k = 0; k < n; ++k) {
     const double ang = pi * static_cast<double>((k * k) % (2 * n)) / static_cast<double>(n);   // k^2 mod 2N: exact
     const double cs = std::cos(ang), sn = std::sin(ang);
@@ -162,7 +169,12 @@ int ensure_bluestein(int dev, int64_t n, cudaStream_t stream, BluesteinTables* t
   AMC_CUDA(cudaMemcpyAsync(t.chirp, chirp.data(), static_cast<size_t>(n) * sizeof(float2), cudaMemcpyHostToDevice, stream));
   AMC_CUDA(cudaMemcpyAsync(t.bfft, bf.data(), static_cast<size_t>(m) * sizeof(float2), cudaMemcpyHostToDevice, stream));
   AMC_CUDA(cudaStreamSynchronize(stream));   // once per (device, N): later calls on other streams rely on it
-  g_bluestein[{dev, n}] = t;
+  try {
+    g_bluestein[{dev, n}] = t;
+  } catch (...) {
+    // not cached: the tables stay allocated and are used by this call only (a leak of <= 192 KB in an
+    // out-of-memory situation is preferable to freeing memory a queued kernel still reads)
+  }
   *tab = t;
   return AMC_OK;
 }
@@ -506,45 +518,46 @@ int host_copy_threads() {
   return n;
 }
 
-// dst[r * dst_pitch .. + row_bytes) = src[r * src_pitch .. + row_bytes) for r < n_rows, rows spread over host threads
+// dst[r * dst_pitch .. + row_bytes) = src[r * src_pitch .. + row_bytes) for r < n_rows, spread over host threads.
+// Never throws (the C ABI must not): whatever could not be handed to a thread is copied by the caller.
 void gather_rows(unsigned char* dst, size_t dst_pitch, const unsigned char* src, size_t src_pitch, size_t row_bytes,
                  size_t n_rows) {
-  const size_t total = row_bytes * n_rows;
-  int nt = host_copy_threads();
-  if (total < (4u << 20) || nt <= 1) nt = 1;
-  auto work = [=](size_t r0, size_t r1) {
-    if (dst_pitch == row_bytes && src_pitch == row_bytes) {
-      std::memcpy(dst + r0 * row_bytes, src + r0 * row_bytes, (r1 - r0) * row_bytes);
+  const bool linear = (dst_pitch == row_bytes && src_pitch == row_bytes) || n_rows == 1;
+  // unit of work: bytes of one contiguous block, or rows
+  const size_t units = linear ? row_bytes * n_rows : n_rows;
+  auto work = [=](size_t u0, size_t u1) {
+    if (linear) {
+      std::memcpy(dst + u0, src + u0, u1 - u0);
     } else {
-      for (size_t r = r0; r < r1; ++r) std::memcpy(dst + r * dst_pitch, src + r * src_pitch, row_bytes);
+      for (size_t r = u0; r < u1; ++r) std::memcpy(dst + r * dst_pitch, src + r * src_pitch, row_bytes);
     }
   };
-  if (nt == 1) {
-    work(0, n_rows);
+  size_t nt = static_cast<size_t>(host_copy_threads());
+  if (row_bytes * n_rows < (4u << 20)) nt = 1;
+  if (nt > units) nt = units;
+  if (nt <= 1) {
+    work(0, units);
     return;
   }
-  if (n_rows < static_cast<size_t>(nt)) {   // few long rows (one contiguous block): split by bytes instead
-    if (n_rows == 1 || (dst_pitch == row_bytes && src_pitch == row_bytes)) {
-      const size_t per = (total + nt - 1) / nt;
-      std::vector<std::thread> th;
-      for (int t = 0; t < nt; ++t) {
-        const size_t b0 = per * t, b1 = (b0 + per < total) ? b0 + per : total;
-        if (b0 >= b1) break;
-        th.emplace_back([=] { std::memcpy(dst + b0, src + b0, b1 - b0); });
+  const size_t per = (units + nt - 1) / nt;
+  size_t handed = per;                      // the caller copies the first share itself
+  {
+    std::thread th[64];
+    size_t started = 0;
+    try {
+      for (size_t t = 1; t < nt && handed < units; ++t) {
+        const size_t u0 = handed, u1 = (u0 + per < units) ? u0 + per : units;
+        th[started] = std::thread(work, u0, u1);
+        ++started;
+        handed = u1;
       }
-      for (auto& t : th) t.join();
-      return;
+    } catch (...) {
+      // thread creation failed: the remaining shares are copied below
     }
-    nt = static_cast<int>(n_rows);
+    work(0, per < units ? per : units);
+    for (size_t t = 0; t < started; ++t) th[t].join();
   }
-  std::vector<std::thread> th;
-  const size_t per = (n_rows + nt - 1) / nt;
-  for (int t = 0; t < nt; ++t) {
-    const size_t r0 = per * t, r1 = (r0 + per < n_rows) ? r0 + per : n_rows;
-    if (r0 >= r1) break;
-    th.emplace_back(work, r0, r1);
-  }
-  for (auto& t : th) t.join();
+  if (handed < units) work(handed, units);
 }
 
 }  // namespace
