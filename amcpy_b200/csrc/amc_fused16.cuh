@@ -159,6 +159,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
   constexpr int GROUP = Cfg::GROUP, W = Cfg::W, SPT = Cfg::SPT, M1 = Cfg::M1, LOG_M1 = Cfg::LOG_M1;
   constexpr bool DO_FFT = (PROF & kProfFft) != 0, DO_PHASE = (PROF & kProfPhase) != 0, DO_AMP = (PROF & kProfAmp) != 0,
                  DO_MOM = (PROF & kProfMom) != 0;
+  static_assert(DO_MOM, "every compiled profile keeps the monomial sums: finalize_features detects NaN input from them");
   static_assert(PROF > 0 && PROF <= kProfAll, "unknown feature profile");
   extern __shared__ __align__(128) unsigned char smem_raw[];
 

@@ -39,6 +39,7 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
   // feature groups of this instantiation (feature_mask profiles, see amc_device.cuh: kProf*)
   constexpr bool DO_FFT = (PROF & kProfFft) != 0, DO_PHASE = (PROF & kProfPhase) != 0, DO_AMP = (PROF & kProfAmp) != 0,
                  DO_MOM = (PROF & kProfMom) != 0;
+  static_assert(DO_MOM, "every compiled profile keeps the monomial sums: finalize_features detects NaN input from them");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int g = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

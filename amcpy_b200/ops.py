@@ -9,6 +9,7 @@ import numpy as np
 from . import _native as nat
 
 N_FEATURES = 18
+FUSED_SIZES = (256, 512, 1024, 2048, 4096, 8192, 16384)   # frame sizes with a fused kernel (amc_api.cu: fused_size)
 MOMENT_NAMES = ("m20", "m21", "m22", "m40", "m41", "m42", "m43", "m60", "m61", "m62", "m63")
 
 
@@ -60,7 +61,7 @@ def feature_mask_of(feature_ids) -> int:
 
 
 def extract_features(iq, out=None, stream=None, force_general: bool = False, feature_mask: int = nat.AMC_ALL_FEATURES,
-                     spt8: bool = False, ws: bool = False, direct_dft: bool = False):
+                     spt8: bool = False, ws: bool = False, direct_dft: bool = False, relayout: bool = True):
     """All 18 features of every frame of a device-resident complex tensor.
 
     feature_mask (default: all 18): the features the caller will read.  The library may skip the work of
@@ -72,6 +73,8 @@ def extract_features(iq, out=None, stream=None, force_general: bool = False, fea
     out : optional CUDA float64 tensor (..., 18), C-contiguous.
     spt8: A/B switch - run the first-generation 8-samples-per-thread fused kernel.
     ws  : A/B switch - run the warp-specialised (FP64 warps / FP32 warps) variant, N = 2048 only.
+    relayout: sample-major device tensors of a fused frame size are re-laid-out into a scratch tensor first
+          (False: the general kernel reads them in place).
     direct_dft: cross-check switch - frame sizes that are not powers of two use the float64 direct DFT (O(N^2))
           instead of the float32 Bluestein FFT of the general kernel.
     Returns float64 (..., 18); column k = feature id k+1.  Enqueued on `stream`
@@ -81,6 +84,11 @@ def extract_features(iq, out=None, stream=None, force_general: bool = False, fea
     lead = tuple(iq.shape[:-1]) if iq.dim() > 1 else (1,)
     x = _as_frames_2d(iq)
     n_frames, n = x.shape
+    if (relayout and not force_general and n in FUSED_SIZES and n_frames > 1 and x.stride(0) == 1
+            and x.stride(1) >= n_frames):
+        # sample-major on the device (a loadmat-ordered block): one pass of the library's re-layout kernel, then the
+        # fused kernel, instead of the general kernel in place (17x slower); costs a scratch copy of the batch
+        x = frames_from_sample_major(x, n_frames, n, x.stride(1), stream=stream)
     if out is None:
         out = torch.empty((n_frames, N_FEATURES), dtype=torch.float64, device=x.device)
     else:

@@ -164,6 +164,9 @@ def test_nan_samples_poison_their_frame_and_only_their_frame(torch_cuda, n):
         assert np.isnan(got[list(bad)]).all(), (n, force)
         good = np.delete(np.arange(40), list(bad))
         assert_features_close(got[good], want[good])
+    # the reduced feature profiles apply the same rule
+    got = ops.extract_features(torch_cuda.from_numpy(x).cuda(), feature_mask=ops.feature_mask_of([2, 6, 12])).cpu().numpy()
+    assert np.isnan(got[list(bad)]).all() and np.isfinite(got[good][:, [1, 5, 11]]).all()
 
 
 def test_warp_specialised_variant_is_bitwise_the_default_kernel(torch_cuda):
