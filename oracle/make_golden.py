@@ -32,6 +32,7 @@ from amcpy.features import (  # noqa: E402
 )
 
 from amcpy_b200 import synth  # noqa: E402
+from oracle.hard_cases import HARD_SIZES, hard_case_inputs  # noqa: E402
 
 GOLD = ROOT / "tests" / "golden"
 SEED = 2024
@@ -48,8 +49,21 @@ def ref_features(frames: np.ndarray) -> np.ndarray:
         return np.array([calculate_features(IDS, f) for f in frames], dtype=np.float64)
 
 
+def hard_cases() -> None:
+    """Outputs of the unmodified reference on oracle/hard_cases.py: non-power-of-two sizes (pocketfft takes any
+    length), carrier offset / DC / scale, complex64 input (numpy computes it in float32), frames holding a NaN."""
+    for n in HARD_SIZES:
+        x = hard_case_inputs(n)
+        x64 = x[:4].astype(np.complex64)
+        np.savez(GOLD / f"hard_n{n}.npz", n=n, input_sha256=sha(x), features=ref_features(x),
+                 features_c64=ref_features(x64))
+
+
 def main() -> None:
     GOLD.mkdir(parents=True, exist_ok=True)
+    if "--hard-only" in sys.argv:      # leaves the other fixtures (and their zip timestamps) untouched
+        hard_cases()
+        return
 
     # 1. the reference's own 10-sample fixture: features + helper types
     sig = _test_signal()
@@ -111,6 +125,9 @@ def main() -> None:
             out[f"{mod}_matrix"] = m[key]
             out[f"{mod}_modulation"] = m["Modulation"]
         np.savez(GOLD / "stage_16x2x2048.npz", **out)
+
+    # 6. hard cases
+    hard_cases()
 
     for p in sorted(GOLD.glob("*.npz")):
         print(p.name, os.path.getsize(p))

@@ -73,6 +73,21 @@ def test_oracle_on_ragged_sizes(n):
     assert np.allclose(orc.features_batch(x), want, rtol=1e-14, atol=0)
 
 
+@pytest.mark.parametrize("n", [127, 129, 1536, 2047, 2048, 6000, 8191])
+def test_oracle_on_hard_cases_from_the_reference(n):
+    """Non-power-of-two sizes, carrier offset / DC / scale, NaN frames, complex64 input: the oracle restates what the
+    unmodified reference returned (tests/golden/hard_n*.npz)."""
+    from conftest import golden_hard
+
+    x, want, want64 = golden_hard(n)
+    with np.errstate(all="ignore"):
+        got = orc.features_batch(x)
+        got64 = orc.features_batch(x[:4].astype(np.complex64))
+    assert np.isnan(want[8:]).all() and np.isnan(got[8:]).all()           # a NaN poisons all 18 features
+    assert np.allclose(got[:8], want[:8], rtol=1e-13, atol=0)
+    assert np.allclose(got64, want64, rtol=1e-5, atol=0)                    # float32 arithmetic in both
+
+
 def test_helpers_realistic_frame():
     from amcpy_b200 import synth
 
