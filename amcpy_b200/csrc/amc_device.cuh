@@ -129,7 +129,10 @@ __device__ __forceinline__ double unwrap_step(double dd) {
 }
 
 // ------------------------------------------------------------------ float32 atan2 (1e-6 class)
-// atan(q) on [0,1] = q + q*s*P(s), s = q*q, degree-6 P fitted minimax (abs err 5e-8 before rounding).
+// atan(q) on [0,1] = q + q*s*P(s), s = q*q, degree-7 P fitted minimax (abs err 7e-9 before rounding).  One term more
+// than float32 rounding alone would ask for: the equi-oscillating error of the degree-6 fit (5e-8, period ~0.1 rad)
+// has a local SLOPE of ~1e-6, which is the relative error it puts on the standard deviation of a narrow phase cluster
+// (unmodulated carrier / strong DC line at high SNR: found by tools/soak.py, 1.2e-6 on features 2 and 3).
 // Predicate-free octant / quadrant fix-ups (FSET.BF + sign-bit masks) so that many evaluations can
 // be interleaved without spilling predicates.  atan2(+-0, +-0) follows IEEE / np.angle.
 __device__ __forceinline__ float atan2_fast(float y, float x) {
@@ -139,13 +142,14 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
   const float q = mn * rc;
   const float s = q * q;
-  float p = -0.004355369135737419f;
-  p = fmaf(p, s, 0.023040004074573517f);
-  p = fmaf(p, s, -0.0577734000980854f);
-  p = fmaf(p, s, 0.09794221073389053f);
-  p = fmaf(p, s, -0.13976576924324036f);
-  p = fmaf(p, s, 0.19962702691555023f);
-  p = fmaf(p, s, -0.3333165943622589f);
+  float p = 0.0026222064831683623f;
+  p = fmaf(p, s, -0.015132382451695708f);
+  p = fmaf(p, s, 0.0411216062546977f);
+  p = fmaf(p, s, -0.07366684174003307f);
+  p = fmaf(p, s, 0.10573921500635099f);
+  p = fmaf(p, s, -0.14185972498001842f);
+  p = fmaf(p, s, 0.19990396259243107f);
+  p = fmaf(p, s, -0.33332987041851964f);
   float r = fmaf(q * s, p, q);                              // [0, pi/4]
   const float swap = (ay > ax) ? 1.0f : 0.0f;               // FSET.BF
   r = fabsf(fmaf(swap, -kPiO2F, r));                        // ay > ax: pi/2 - r
