@@ -35,6 +35,28 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert built_lib.amc_launch_count() == 0
 
 
+def test_python_constants_mirror_the_header():
+    """Every `#define AMC_*` of include/amcpy_b200.h has the same value in the ctypes binding, and the feature-mask
+    helper maps ids to the header's bit convention (bit k = feature id k+1)."""
+    from amcpy_b200 import _native as nat
+    from amcpy_b200 import ops
+
+    header = (ROOT / "include" / "amcpy_b200.h").read_text()
+    defines = dict(re.findall(r"#define\s+(AMC_[A-Z0-9_]+)\s+\(?(-?(?:0x[0-9A-Fa-f]+|\d+))u?\)?", header))
+    assert {"AMC_OK", "AMC_ERR_INVALID_ARG", "AMC_C128", "AMC_ALL_FEATURES", "AMC_FLAG_DIRECT_DFT"} <= set(defines)
+    for name, text in defines.items():
+        if hasattr(nat, name):
+            assert getattr(nat, name) == int(text, 0), name
+    for name in ("AMC_C64", "AMC_C128", "AMC_ALL_FEATURES", "AMC_FLAG_FORCE_GENERAL", "AMC_FLAG_FUSED_SPT8",
+                 "AMC_FLAG_FUSED_WS", "AMC_FLAG_DIRECT_DFT"):
+        assert hasattr(nat, name), name
+    assert ops.feature_mask_of(range(1, 19)) == nat.AMC_ALL_FEATURES
+    assert ops.feature_mask_of([1]) == 1 and ops.feature_mask_of([18]) == 1 << 17
+    assert ops.feature_mask_of([2, 4, 6, 8, 12, 14]) == 0b10100010101010
+    with pytest.raises(KeyError):
+        ops.feature_mask_of([19])
+
+
 def test_no_cuda_device_is_an_error_not_a_fallback(built_lib):
     import torch
 
