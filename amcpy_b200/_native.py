@@ -73,6 +73,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+def build_if_missing() -> Path:
+    """Build only when the library file is absent (a checkout that received sources but no build products).
+    Unlike `build()` it never rebuilds a library that merely looks older than a source file."""
+    if os.environ.get("AMCPY_B200_LIB") or LIB_PATH.exists():
+        return LIB_PATH
+    return build(force=True)
+
+
 _LIB = None
 
 _P = ctypes.c_void_p

@@ -225,6 +225,13 @@ def run_cuda_arm(args):
         if world == 1 and args.gpus > 1:
             print(f"bench.py --gpus {args.gpus} must be launched with torchrun (one rank per GPU)", file=sys.stderr)
             return 2
+    if local_rank == 0:
+        nat.build_if_missing()   # the .so normally travels with the snapshot; a source-only checkout builds it once
+    else:
+        for _ in range(600):     # other ranks wait for rank 0's build instead of compiling the same file
+            if nat.LIB_PATH.exists():
+                break
+            time.sleep(0.5)
     nat.require_cuda()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
