@@ -63,3 +63,20 @@ def test_random_frames_complex64_input_equals_widened_complex128(n, frames):
     for fid in range(1, 19):
         rel = np.nanmax(np.abs(g[:, fid - 1] - want[:, fid - 1]) / np.abs(want[:, fid - 1]))
         assert rel <= orc.RTOL[fid], f"N={n} feature {fid}: rel err {rel:.3e}"
+
+
+def test_randomised_soak_prefix():
+    """The first 150 cases of tools/soak.py, seed 1 (a deterministic sequence): random frame sizes incl. non-powers of
+    two, batch sizes, dtypes, scales 1e-4..1e4, carrier / DC offsets, layouts (contiguous, padded, sample-major, host
+    pipeline) and feature masks against the oracle."""
+    import json
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    res = subprocess.run([sys.executable, str(ROOT / "tools" / "soak.py"), "--cases", "150", "--seed", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+    summary = json.loads(res.stdout.strip().splitlines()[-1])
+    assert summary["soak"] == "ok" and summary["cases"] == 150

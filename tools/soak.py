@@ -1,7 +1,7 @@
 """Randomised soak of the CUDA path against the numpy oracle (test infrastructure, like tests/): random frame sizes
 (every fused size, random other sizes up to 8192), batch sizes, dtypes, scales, carrier / DC offsets, SNRs, memory
 layouts (contiguous, padded rows, sample-major, host pipeline) and feature masks, for a time budget.
-usage: python tools/soak.py [--seconds 120] [--seed 1]   -> one JSON summary line, exit 1 on the first mismatch"""
+usage: python tools/soak.py [--seconds 120 | --cases 150] [--seed 1]   -> one JSON summary line, exit 1 on the first mismatch"""
 import argparse
 import json
 import sys
@@ -19,6 +19,7 @@ from oracle import amc_oracle as orc  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=120.0)
 ap.add_argument("--seed", type=int, default=1)
+ap.add_argument("--cases", type=int, default=0, help="stop after this many cases instead of after --seconds")
 args = ap.parse_args()
 rng = np.random.default_rng(args.seed)
 FUSED = [256, 512, 1024, 2048, 4096, 8192, 16384]
@@ -53,7 +54,7 @@ def check(got, want, what, loose):
 t_end = time.time() + args.seconds
 cases = frames_total = 0
 kinds = {}
-while time.time() < t_end:
+while (cases < args.cases) if args.cases > 0 else (time.time() < t_end):
     n = int(rng.choice(FUSED)) if rng.random() < 0.7 else int(rng.integers(8, 8193))
     nf = int(rng.integers(1, max(2, min(200, 400000 // n))))
     c64 = rng.random() < 0.3
