@@ -46,6 +46,25 @@ def _library_present():
         nat.build_if_missing()
 
 
+def run_c_example(tmp_path, n_frames=64):
+    """Compile examples/extract_host.c with gcc against the built library and run it; returns CompletedProcess."""
+    import shutil
+    import subprocess
+
+    from amcpy_b200 import _native as nat
+
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    exe = tmp_path / "extract_host"
+    lib_dir = nat.LIB_PATH.parent
+    cmd = [gcc, "-O2", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "extract_host.c"), "-o", str(exe),
+           f"-L{lib_dir}", "-lamcpy_b200", "-lm", f"-Wl,-rpath,{lib_dir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    return subprocess.run([str(exe), str(n_frames)], capture_output=True, text=True, timeout=300)
+
+
 def sha(a) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 

@@ -331,6 +331,18 @@ def test_feature_mask_is_ignored_where_no_reduced_profile_exists(torch_cuda):
         ops.feature_mask_of([0])
 
 
+def test_plain_c_host_runs_the_hot_path(torch_cuda, tmp_path):
+    """examples/extract_host.c: a C program with host buffers through amc_extract_host - QPSK cumulants come out
+    where theory puts them (|C20| ~ 0, |C40| ~ 1, |C42| ~ 1) and the kernels were launched by the library."""
+    from conftest import run_c_example
+
+    res = run_c_example(tmp_path, 256)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "frame 0:" in res.stdout and "mean |C20|" in res.stdout
+    launches = int(res.stdout.rsplit(";", 1)[1].split()[0])
+    assert launches >= 1
+
+
 # ------------------------------------------------------------------ C ABI error behaviour
 def test_c_abi_error_codes(torch_cuda):
     from amcpy_b200 import _native as nat

@@ -57,6 +57,20 @@ def test_python_constants_mirror_the_header():
         ops.feature_mask_of([19])
 
 
+def test_plain_c_host_links_against_the_abi(built_lib, tmp_path):
+    """examples/extract_host.c (no Python, no torch) compiles with -Wall -Werror against include/amcpy_b200.h and the
+    library; without a device it stops after the ABI checks that need no GPU and says so (no CPU compute path)."""
+    import torch
+
+    from conftest import run_c_example
+
+    res = run_c_example(tmp_path, 8)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "ABI version" in res.stdout and "iq_dtype 99 unknown" in res.stdout
+    if not torch.cuda.is_available():
+        assert "no CUDA device" in res.stdout and "frame 0:" not in res.stdout
+
+
 def test_no_cuda_device_is_an_error_not_a_fallback(built_lib):
     import torch
 
