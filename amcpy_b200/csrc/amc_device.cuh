@@ -132,7 +132,7 @@ __device__ __forceinline__ double unwrap_step(double dd) {
 // atan(q) on [0,1] = q + q*s*P(s), s = q*q, degree-7 P fitted minimax (abs err 7e-9 before rounding).  One term more
 // than float32 rounding alone would ask for: the equi-oscillating error of the degree-6 fit (5e-8, period ~0.1 rad)
 // has a local SLOPE of ~1e-6, which is the relative error it puts on the standard deviation of a narrow phase cluster
-// (unmodulated carrier / strong DC line at high SNR: found by tools/soak.py, 1.2e-6 on features 2 and 3).
+// (unmodulated carrier / strong DC line at high SNR: found by tests/soak.py, 1.2e-6 on features 2 and 3).
 // Predicate-free octant / quadrant fix-ups (FSET.BF + sign-bit masks) so that many evaluations can
 // be interleaved without spilling predicates.  atan2(+-0, +-0) follows IEEE / np.angle.
 __device__ __forceinline__ float atan2_fast(float y, float x) {

@@ -1,7 +1,7 @@
 """One-off check that the CPU baseline `bench.py` reports (the oracle's faithful restatement, kind "port") runs at the
 speed of the UNMODIFIED reference: both are timed here, single-threaded, on the same frames.  Needs /root/reference
 (only present in the build container - not on the GPU box), so the result is committed under profiles/.
-usage: PYTHONDONTWRITEBYTECODE=1 python tools/ref_vs_port_timing.py [frames] > profiles/r1n_ref_vs_port_cpu.json"""
+usage: PYTHONDONTWRITEBYTECODE=1 python oracle/ref_vs_port_timing.py [frames] > profiles/r1n_ref_vs_port_cpu.json"""
 import json
 import sys
 import time

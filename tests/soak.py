@@ -1,7 +1,8 @@
-"""Randomised soak of the CUDA path against the numpy oracle (test infrastructure, like tests/): random frame sizes
+"""Randomised soak of the CUDA path against the numpy oracle (test infrastructure; not collected by pytest itself,
+tests/test_gpu_fuzz.py runs a deterministic prefix of it): random frame sizes
 (every fused size, random other sizes up to 8192), batch sizes, dtypes, scales, carrier / DC offsets, SNRs, memory
 layouts (contiguous, padded rows, sample-major, host pipeline) and feature masks, for a time budget.
-usage: python tools/soak.py [--seconds 120 | --cases 150] [--seed 1]   -> one JSON summary line, exit 1 on the first mismatch"""
+usage: python tests/soak.py [--seconds 120 | --cases 150] [--seed 1]   -> one JSON summary line, exit 1 on the first mismatch"""
 import argparse
 import json
 import sys

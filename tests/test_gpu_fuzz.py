@@ -66,7 +66,7 @@ def test_random_frames_complex64_input_equals_widened_complex128(n, frames):
 
 
 def test_randomised_soak_prefix():
-    """The first 150 cases of tools/soak.py, seed 1 (a deterministic sequence): random frame sizes incl. non-powers of
+    """The first 150 cases of tests/soak.py, seed 1 (a deterministic sequence): random frame sizes incl. non-powers of
     two, batch sizes, dtypes, scales 1e-4..1e4, carrier / DC offsets, layouts (contiguous, padded, sample-major, host
     pipeline) and feature masks against the oracle."""
     import json
@@ -75,7 +75,7 @@ def test_randomised_soak_prefix():
 
     from conftest import ROOT
 
-    res = subprocess.run([sys.executable, str(ROOT / "tools" / "soak.py"), "--cases", "150", "--seed", "1"],
+    res = subprocess.run([sys.executable, str(ROOT / "tests" / "soak.py"), "--cases", "150", "--seed", "1"],
                          capture_output=True, text=True, timeout=600, cwd=str(ROOT))
     assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
     summary = json.loads(res.stdout.strip().splitlines()[-1])
