@@ -21,9 +21,9 @@ HEADER = PKG.parent / "include" / "amcpy_b200.h"
 
 AMC_C64, AMC_C128 = 0, 1
 AMC_FLAG_FORCE_GENERAL = 1
-AMC_FLAG_FUSED_SPT8 = 2
-AMC_FLAG_FUSED_WS = 4
 AMC_FLAG_DIRECT_DFT = 8
+AMC_FLAG_FUSED_SPT8 = 2   # only understood by a library built with -DAMC_EXPERIMENTS (tools/exp/build_variants.py)
+AMC_FLAG_FUSED_WS = 4     # idem
 AMC_ALL_FEATURES = 0x3FFFF
 
 NVCC_FLAGS = [
@@ -39,7 +39,7 @@ class AmcError(RuntimeError):
 
 
 def _sources():
-    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [HEADER]
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.rglob("*.cuh")) + [HEADER]
 
 
 def needs_build() -> bool:
@@ -49,16 +49,27 @@ def needs_build() -> bool:
     return any(s.stat().st_mtime > built for s in _sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile csrc/*.cu for sm_100a into _lib/libamcpy_b200.so (nvcc cross-compiles without a GPU)."""
+def build(force: bool = False, verbose: bool = False, defines=(), out: Path | None = None) -> Path:
+    """Compile csrc/*.cu for sm_100a into _lib/libamcpy_b200.so (nvcc cross-compiles without a GPU).
+    `defines` / `out`: A/B builds only (e.g. defines=("AMC_EXPERIMENTS",), out=_lib/exp/libamcpy_b200_exp.so,
+    selected at run time with AMCPY_B200_LIB)."""
+    if out is not None:
+        return _compile(Path(out), verbose, defines)
     if not force and not needs_build():
         return LIB_PATH
+    path = _compile(LIB_PATH, verbose, defines)
+    global _LIB
+    _LIB = None
+    return path
+
+
+def _compile(target: Path, verbose: bool, defines) -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build the amcpy_b200 CUDA library")
-    LIB_DIR.mkdir(parents=True, exist_ok=True)
-    tmp = LIB_DIR / f".libamcpy_b200.{os.getpid()}.so"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(tmp)] + [str(p) for p in sorted(CSRC.glob("*.cu"))]
+    target.parent.mkdir(parents=True, exist_ok=True)
+    tmp = target.parent / f".{target.stem}.{os.getpid()}.so"
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", str(tmp)] + [str(p) for p in sorted(CSRC.glob("*.cu"))]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -67,10 +78,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    os.replace(tmp, LIB_PATH)
-    global _LIB
-    _LIB = None
-    return LIB_PATH
+    os.replace(tmp, target)
+    return target
 
 
 def build_if_missing() -> Path:
@@ -91,6 +100,8 @@ _U32 = ctypes.c_uint32
 # name -> (restype, argtypes); must list every symbol include/amcpy_b200.h declares
 SIGNATURES = {
     "amc_version": (_INT, []),
+    "amc_init": (_INT, [_INT]),
+    "amc_workspace_bytes": (_I64, [_INT, _I64, _I64, _INT]),
     "amc_last_error_string": (ctypes.c_char_p, []),
     "amc_device_count": (_INT, []),
     "amc_launch_count": (_I64, []),

@@ -14,10 +14,15 @@
 #include <utility>
 #include <vector>
 
+#include <atomic>
+#include <condition_variable>
+
 #include "amc_fused.cuh"
 #include "amc_fused16.cuh"
 #include "amc_fusedw.cuh"
-#include "amc_fusedws.cuh"
+#ifdef AMC_EXPERIMENTS
+#include "experiments/amc_fusedws.cuh"
+#endif
 #include "amc_large.cuh"
 #include "amc_general.cuh"
 #include "amc_generate.cuh"
@@ -26,6 +31,7 @@ namespace {
 
 thread_local std::string t_err;
 thread_local int64_t t_launches = 0;
+std::atomic<unsigned long long> g_ticket{1};   // unique, increasing id of every fused launch (amc_device.cuh: g_redo_ring)
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -46,12 +52,31 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kMaxDevices = 64;
 std::mutex g_mu;
-bool g_tw_ready[kMaxDevices] = {};
-int g_sm_count[kMaxDevices] = {};
+
+// Per-device library state.  Tables are built on an internal stream and published through an event: callers'
+// streams wait for the event on the device (cudaStreamWaitEvent) - no host-side synchronisation, nothing is ever
+// enqueued on the caller's stream except its own kernels - until the event is known to have completed.
+struct DeviceState {
+  int sms = 0;
+  bool tw_launched = false;
+  bool tw_done = false;
+  cudaStream_t init_stream = nullptr;
+  cudaEvent_t tw_event = nullptr;
+};
+DeviceState g_dev[kMaxDevices];
 
 struct DevInfo {
   int dev;
   int sms;
+};
+
+// Restores the caller's current device on every exit path of the host entries.
+struct DeviceGuard {
+  int prev = -1;
+  bool armed = false;
+  ~DeviceGuard() {
+    if (armed) cudaSetDevice(prev);
+  }
 };
 
 int device_info(DevInfo* di) {
@@ -59,28 +84,57 @@ int device_info(DevInfo* di) {
   AMC_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= kMaxDevices) return fail(AMC_ERR_INVALID_ARG, "device index %d out of range", dev);
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_sm_count[dev] == 0) {
+  if (g_dev[dev].sms == 0) {
     int sms = 0;
     AMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    g_sm_count[dev] = sms;
+    g_dev[dev].sms = sms;
   }
   di->dev = dev;
-  di->sms = g_sm_count[dev];
+  di->sms = g_dev[dev].sms;
+  return AMC_OK;
+}
+
+// internal stream of the current device (g_mu held)
+int init_stream_locked(DeviceState& d) {
+  if (!d.init_stream) AMC_CUDA(cudaStreamCreateWithFlags(&d.init_stream, cudaStreamNonBlocking));
+  return AMC_OK;
+}
+
+// `stream` will see the tables: either they are known to be complete, or the stream waits for their event.
+int wait_for_event(cudaStream_t stream, cudaEvent_t ev, bool* done_flag) {
+  const cudaError_t q = cudaEventQuery(ev);
+  if (q == cudaSuccess) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    *done_flag = true;
+    return AMC_OK;
+  }
+  if (q != cudaErrorNotReady) return fail(AMC_ERR_CUDA, "table initialisation failed: %s", cudaGetErrorString(q));
+  AMC_CUDA(cudaStreamWaitEvent(stream, ev, 0));
   return AMC_OK;
 }
 
 int ensure_twiddles(int dev, cudaStream_t stream) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (g_tw_ready[dev]) return AMC_OK;
-  amc::init_twiddle16_kernel<<<26, 256, 0, stream>>>();
-  amc::init_twiddle16dif_kernel<<<29, 256, 0, stream>>>();
-  amc::init_twiddle8_kernel<<<22, 256, 0, stream>>>();
-  amc::init_twiddle_large_kernel<<<64, 256, 0, stream>>>();
-  t_launches += 4;
-  AMC_CUDA(cudaGetLastError());
-  AMC_CUDA(cudaStreamSynchronize(stream));  // once per device: later calls on other streams may rely on it
-  g_tw_ready[dev] = true;
-  return AMC_OK;
+  cudaEvent_t ev;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceState& d = g_dev[dev];
+    if (d.tw_done) return AMC_OK;
+    if (!d.tw_launched) {
+      int rc = init_stream_locked(d);
+      if (rc != AMC_OK) return rc;
+      if (!d.tw_event) AMC_CUDA(cudaEventCreateWithFlags(&d.tw_event, cudaEventDisableTiming));
+      amc::init_twiddle16_kernel<<<26, 256, 0, d.init_stream>>>();
+      amc::init_twiddle16dif_kernel<<<29, 256, 0, d.init_stream>>>();
+      amc::init_twiddle8_kernel<<<22, 256, 0, d.init_stream>>>();
+      amc::init_twiddle_large_kernel<<<64, 256, 0, d.init_stream>>>();
+      t_launches += 4;
+      AMC_CUDA(cudaGetLastError());
+      AMC_CUDA(cudaEventRecord(d.tw_event, d.init_stream));
+      d.tw_launched = true;
+    }
+    ev = d.tw_event;
+  }
+  return wait_for_event(stream, ev, &g_dev[dev].tw_done);
 }
 
 bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -95,6 +149,8 @@ struct BluesteinTables {
   float2* chirp = nullptr;   // N
   float2* bfft = nullptr;    // M
   int m = 0;
+  cudaEvent_t ready = nullptr;
+  bool done = false;
 };
 std::map<std::pair<int, int64_t>, BluesteinTables> g_bluestein;
 constexpr size_t kBluesteinMaxEntries = 64;          // beyond that many distinct sizes: direct DFT
@@ -122,63 +178,138 @@ void host_fft_pow2(std::vector<std::complex<double>>& v) {
   }
 }
 
-// returns AMC_OK with tab->m == 0 when this size should use the direct DFT instead
-int ensure_bluestein(int dev, int64_t n, cudaStream_t stream, BluesteinTables* tab) {
-  *tab = BluesteinTables();
-  if (n < kBluesteinMinN) return AMC_OK;
+int64_t bluestein_m(int64_t n) {
+  if (n < kBluesteinMinN) return 0;
   int64_t m = 1;
   while (m < 2 * n - 1) m <<= 1;
-  if (m > kBluesteinMaxM) return AMC_OK;
-  std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_bluestein.find({dev, n});
-  if (it != g_bluestein.end()) {
-    *tab = it->second;
-    return AMC_OK;
+  return m > kBluesteinMaxM ? 0 : m;
+}
+
+// returns AMC_OK with tab->m == 0 when this size should use the direct DFT instead.  The tables are uploaded on the
+// library's internal stream; `stream` waits for them on the device (no host synchronisation).
+int ensure_bluestein(int dev, int64_t n, cudaStream_t stream, BluesteinTables* tab) {
+  *tab = BluesteinTables();
+  const int64_t m = bluestein_m(n);
+  if (m == 0) return AMC_OK;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_bluestein.find({dev, n});
+    if (it != g_bluestein.end()) {
+      *tab = it->second;
+    } else if (g_bluestein.size() >= kBluesteinMaxEntries) {
+      return AMC_OK;
+    }
   }
-  if (g_bluestein.size() >= kBluesteinMaxEntries) return AMC_OK;
-  const double pi = std::acos(-1.0);
-  std::vector<std::complex<double>> b;
-  std::vector<float2> chirp, bf;
-  try {
-    b.resize(static_cast<size_t>(m));
-    chirp.resize(static_cast<size_t>(n));
-    bf.resize(static_cast<size_t>(m));
-  } catch (...) {
-    return AMC_OK;   // no host memory for the tables: the direct DFT needs none
+  if (tab->m == 0) {
+    // host-side construction outside the lock (other threads / devices keep running); a racing thread building the
+    // same table loses at insertion time and frees its copy
+    const double pi = std::acos(-1.0);
+    std::vector<std::complex<double>> b;
+    std::vector<float2> chirp, bf;
+    try {
+      b.resize(static_cast<size_t>(m));
+      chirp.resize(static_cast<size_t>(n));
+      bf.resize(static_cast<size_t>(m));
+    } catch (...) {
+      return AMC_OK;   // no host memory for the tables: the direct DFT needs none
+    }
+    for (int64_t k = 0; k < n; ++k) {
+      const double ang = pi * static_cast<double>((k * k) % (2 * n)) / static_cast<double>(n);   // k^2 mod 2N: exact
+      const double cs = std::cos(ang), sn = std::sin(ang);
+      chirp[static_cast<size_t>(k)] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
+      b[static_cast<size_t>(k)] = {cs, sn};
+      if (k > 0) b[static_cast<size_t>(m - k)] = {cs, sn};
+    }
+    host_fft_pow2(b);
+    int bits = 0;
+    while ((int64_t{1} << bits) < m) ++bits;
+    for (int64_t j = 0; j < m; ++j) {
+      int64_t r = 0;
+      for (int q = 0; q < bits; ++q) r |= ((j >> q) & 1) << (bits - 1 - q);
+      const std::complex<double> v = b[static_cast<size_t>(r)] / static_cast<double>(m);
+      bf[static_cast<size_t>(j)] = make_float2(static_cast<float>(v.real()), static_cast<float>(v.imag()));
+    }
+    BluesteinTables t;
+    t.m = static_cast<int>(m);
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_bluestein.find({dev, n});
+    if (it != g_bluestein.end()) {
+      *tab = it->second;                             // another thread was faster
+    } else {
+      DeviceState& d = g_dev[dev];
+      int rc = init_stream_locked(d);
+      if (rc != AMC_OK) return rc;
+      cudaError_t e = cudaMalloc(&t.chirp, static_cast<size_t>(n) * sizeof(float2));
+      if (e == cudaSuccess) e = cudaMalloc(&t.bfft, static_cast<size_t>(m) * sizeof(float2));
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t.ready, cudaEventDisableTiming);
+      // (pageable sources: the runtime has staged the bytes by the time cudaMemcpyAsync returns)
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(t.chirp, chirp.data(), static_cast<size_t>(n) * sizeof(float2), cudaMemcpyHostToDevice, d.init_stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(t.bfft, bf.data(), static_cast<size_t>(m) * sizeof(float2), cudaMemcpyHostToDevice, d.init_stream);
+      if (e == cudaSuccess) e = cudaEventRecord(t.ready, d.init_stream);
+      bool cached = false;
+      if (e == cudaSuccess) {
+        try {
+          g_bluestein[{dev, n}] = t;
+          cached = true;
+        } catch (...) {
+        }
+      }
+      if (!cached) {                                 // nothing may leak: wait for the copies, then free everything
+        cudaStreamSynchronize(d.init_stream);
+        if (t.ready) cudaEventDestroy(t.ready);
+        if (t.chirp) cudaFree(t.chirp);
+        if (t.bfft) cudaFree(t.bfft);
+        if (e != cudaSuccess) return fail(AMC_ERR_CUDA, "Bluestein table upload failed: %s", cudaGetErrorString(e));
+        return AMC_OK;                               // not cacheable (out of host memory): direct DFT for this call
+      }
+      *tab = t;
+    }
   }
-  for (int64_t k = 0; k < n; ++k) {
-    const double ang = pi * static_cast<double>((k * k) % (2 * n)) / static_cast<double>(n);   // k^2 mod 2N: exact
-    const double cs = std::cos(ang), sn = std::sin(ang);
-    chirp[static_cast<size_t>(k)] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
-    b[static_cast<size_t>(k)] = {cs, sn};
-    if (k > 0) b[static_cast<size_t>(m - k)] = {cs, sn};
+  if (!tab->done) {
+    bool done = false;
+    const int rc = wait_for_event(stream, tab->ready, &done);
+    if (rc != AMC_OK) return rc;
+    if (done) {
+      std::lock_guard<std::mutex> lk(g_mu);
+      auto it = g_bluestein.find({dev, n});
+      if (it != g_bluestein.end()) it->second.done = true;
+    }
   }
-  host_fft_pow2(b);
-  int bits = 0;
-  while ((int64_t{1} << bits) < m) ++bits;
-  for (int64_t j = 0; j < m; ++j) {
-    int64_t r = 0;
-    for (int q = 0; q < bits; ++q) r |= ((j >> q) & 1) << (bits - 1 - q);
-    const std::complex<double> v = b[static_cast<size_t>(r)] / static_cast<double>(m);
-    bf[static_cast<size_t>(j)] = make_float2(static_cast<float>(v.real()), static_cast<float>(v.imag()));
-  }
-  BluesteinTables t;
-  t.m = static_cast<int>(m);
-  AMC_CUDA(cudaMalloc(&t.chirp, static_cast<size_t>(n) * sizeof(float2)));
-  AMC_CUDA(cudaMalloc(&t.bfft, static_cast<size_t>(m) * sizeof(float2)));
-  AMC_CUDA(cudaMemcpyAsync(t.chirp, chirp.data(), static_cast<size_t>(n) * sizeof(float2), cudaMemcpyHostToDevice, stream));
-  AMC_CUDA(cudaMemcpyAsync(t.bfft, bf.data(), static_cast<size_t>(m) * sizeof(float2), cudaMemcpyHostToDevice, stream));
-  AMC_CUDA(cudaStreamSynchronize(stream));   // once per (device, N): later calls on other streams rely on it
-  try {
-    g_bluestein[{dev, n}] = t;
-  } catch (...) {
-    // not cached: the tables stay allocated and are used by this call only (a leak of <= 192 KB in an
-    // out-of-memory situation is preferable to freeing memory a queued kernel still reads)
-  }
-  *tab = t;
   return AMC_OK;
 }
 
+// AMCPY_B200_NO_PDL=1: ordinary stream-ordered launches (A/B and debugging)
+bool use_pdl() {
+  static const bool on = [] {
+    const char* env = std::getenv("AMCPY_B200_NO_PDL");
+    return !(env && *env && std::atoi(env) != 0);
+  }();
+  return on;
+}
+
+// Launch with programmatic stream serialisation allowed: the grid may be scheduled while its predecessor in the
+// stream is still running (launch latency, CTA scheduling and the kernel prologue overlap with the predecessor's
+// tail).  Every kernel launched this way executes griddepcontrol.wait (amc_device.cuh: pdl_wait_primary) before its
+// first global-memory access, which blocks until the predecessor has completed and flushed - ordinary stream
+// semantics for everything the kernel reads or writes.
+template <typename... Params, typename... Args>
+cudaError_t launch_pdl(void (*kern)(Params...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(static_cast<unsigned>(block));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Params>(args)...);
+}
+
+#ifdef AMC_EXPERIMENTS
 template <int N, typename CT>
 int launch_fused(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride,
                  int sms, cudaStream_t stream) {
@@ -204,6 +335,8 @@ int launch_fused(const void* iq, int64_t n_frames, int64_t frame_stride, double*
   return AMC_OK;
 }
 
+#endif  // AMC_EXPERIMENTS
+
 // feature_mask -> the cheapest compiled profile of the 16-samples-per-thread kernel that covers it
 // (amc_fused16.cuh: kProf*).  Compiled: moments only, amplitude + moments, everything but the FFT, all.
 int pick_profile(uint32_t feature_mask) {
@@ -221,7 +354,7 @@ int pick_profile(uint32_t feature_mask) {
 
 template <int N, typename CT, int PROF = amc::kProfAll>
 int launch_fused16(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride,
-                   int sms, cudaStream_t stream) {
+                   int sms, cudaStream_t stream, unsigned long long ticket) {
   using Cfg = amc::Fused16Cfg<N, CT>;
   auto kern = amc::fused16_features_kernel<N, CT, PROF>;
   static thread_local int blocks_per_sm[kMaxDevices] = {};
@@ -237,13 +370,13 @@ int launch_fused16(const void* iq, int64_t n_frames, int64_t frame_stride, doubl
   const int64_t want = (n_frames + Cfg::G - 1) / Cfg::G;
   const int64_t cap = static_cast<int64_t>(sms) * blocks_per_sm[dev];
   const int grid = static_cast<int>(want < cap ? want : cap);
-  kern<<<grid, Cfg::CTA, Cfg::SMEM_BYTES, stream>>>(static_cast<const CT*>(iq), n_frames, frame_stride, out,
-                                                   out_stride);
+  AMC_CUDA(launch_pdl(kern, grid, Cfg::CTA, Cfg::SMEM_BYTES, stream, static_cast<const CT*>(iq), n_frames, frame_stride,
+                      out, out_stride, ticket));
   ++t_launches;
-  AMC_CUDA(cudaGetLastError());
   return AMC_OK;
 }
 
+#ifdef AMC_EXPERIMENTS
 template <int N, typename CT>
 int launch_fusedws(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride,
                    int sms, cudaStream_t stream) {
@@ -267,10 +400,11 @@ int launch_fusedws(const void* iq, int64_t n_frames, int64_t frame_stride, doubl
   AMC_CUDA(cudaGetLastError());
   return AMC_OK;
 }
+#endif  // AMC_EXPERIMENTS
 
 template <int N, typename CT, int PROF = amc::kProfAll>
 int launch_fusedw(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride,
-                  int sms, cudaStream_t stream) {
+                  int sms, cudaStream_t stream, unsigned long long ticket) {
   using Cfg = amc::FusedWCfg<N, CT>;
   auto kern = amc::fusedw_features_kernel<N, CT, PROF>;
   static thread_local int blocks_per_sm[kMaxDevices] = {};
@@ -286,82 +420,99 @@ int launch_fusedw(const void* iq, int64_t n_frames, int64_t frame_stride, double
   const int64_t want = (n_frames + Cfg::G - 1) / Cfg::G;
   const int64_t cap = static_cast<int64_t>(sms) * blocks_per_sm[dev];
   const int grid = static_cast<int>(want < cap ? want : cap);
-  kern<<<grid, Cfg::CTA, Cfg::SMEM_BYTES, stream>>>(static_cast<const CT*>(iq), n_frames, frame_stride, out,
-                                                   out_stride);
+  AMC_CUDA(launch_pdl(kern, grid, Cfg::CTA, Cfg::SMEM_BYTES, stream, static_cast<const CT*>(iq), n_frames, frame_stride,
+                      out, out_stride, ticket));
   ++t_launches;
-  AMC_CUDA(cudaGetLastError());
   return AMC_OK;
 }
 
 template <int N, typename CT>
 int launch_large(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride, int sms,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, unsigned long long ticket) {
   using Cfg = amc::LargeCfg<N>;
   auto kern = amc::large_features_kernel<N, CT>;
-  AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  static thread_local bool attr_set[kMaxDevices] = {};
+  int dev = 0;
+  AMC_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {   // once per (thread, device), not on every launch
+    AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[dev] = true;
+  }
   const int64_t cap = static_cast<int64_t>(sms) * Cfg::MIN_BLOCKS;
   const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(static_cast<const CT*>(iq), n_frames, frame_stride, out,
-                                                             out_stride);
+  AMC_CUDA(launch_pdl(kern, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, static_cast<const CT*>(iq), n_frames,
+                      frame_stride, out, out_stride, ticket));
   ++t_launches;
-  AMC_CUDA(cudaGetLastError());
   return AMC_OK;
 }
 
 template <int N, typename CT>
 int launch_fused16_profile(int prof, const void* iq, int64_t n_frames, int64_t frame_stride, double* out,
-                           int64_t out_stride, int sms, cudaStream_t stream) {
+                           int64_t out_stride, int sms, cudaStream_t stream, unsigned long long ticket) {
   switch (prof) {
     case amc::kProfMom:
-      return launch_fused16<N, CT, amc::kProfMom>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      return launch_fused16<N, CT, amc::kProfMom>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
     case amc::kProfAmp | amc::kProfMom:
-      return launch_fused16<N, CT, amc::kProfAmp | amc::kProfMom>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      return launch_fused16<N, CT, amc::kProfAmp | amc::kProfMom>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
     case amc::kProfPhase | amc::kProfAmp | amc::kProfMom:
       return launch_fused16<N, CT, amc::kProfPhase | amc::kProfAmp | amc::kProfMom>(iq, n_frames, frame_stride, out,
-                                                                                     out_stride, sms, stream);
+                                                                                     out_stride, sms, stream, ticket);
     default:
-      return launch_fused16<N, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      return launch_fused16<N, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
   }
 }
 
+// *used_prof receives the feature profile the launched kernel computed (kProfAll unless a reduced profile exists)
 template <typename CT>
 int dispatch_fused(int64_t n, const void* iq, int64_t n_frames, int64_t frame_stride, double* out,
-                   int64_t out_stride, int sms, cudaStream_t stream, bool spt8, bool ws, int prof) {
-  if (ws && n == 2048) return launch_fusedws<2048, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-  if (!spt8 && prof != amc::kProfAll) {   // reduced feature profiles: warp-per-frame and 16-samples-per-thread kernels
-    constexpr int kAM = amc::kProfAmp | amc::kProfMom, kPAM = amc::kProfPhase | kAM;
-    if (n == 256) {
-      if (prof == amc::kProfMom)
-        return launch_fusedw<256, CT, amc::kProfMom>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-      if (prof == kAM) return launch_fusedw<256, CT, kAM>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-      if (prof == kPAM) return launch_fusedw<256, CT, kPAM>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-    }
+                   int64_t out_stride, int sms, cudaStream_t stream, int flags, int prof, int* used_prof,
+                   unsigned long long ticket) {
+  *used_prof = amc::kProfAll;
+#ifdef AMC_EXPERIMENTS
+  if (flags & (AMC_FLAG_FUSED_WS | AMC_FLAG_FUSED_SPT8)) *used_prof = -1;   // experiment kernels carry no ticket
+  if ((flags & AMC_FLAG_FUSED_WS) && n == 2048)
+    return launch_fusedws<2048, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+  if (flags & AMC_FLAG_FUSED_SPT8) {
     switch (n) {
-      case 512: return launch_fused16_profile<512, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream);
-      case 1024: return launch_fused16_profile<1024, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream);
-      case 2048: return launch_fused16_profile<2048, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream);
-      case 4096: return launch_fused16_profile<4096, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 256: return launch_fused<256, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 512: return launch_fused<512, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 1024: return launch_fused<1024, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 2048: return launch_fused<2048, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 4096: return launch_fused<4096, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
       default: break;
     }
   }
-  if (!spt8) {
+#else
+  (void)flags;
+#endif
+  *used_prof = amc::kProfAll;
+  if (prof != amc::kProfAll) {   // reduced feature profiles: warp-per-frame and 16-samples-per-thread kernels
+    constexpr int kAM = amc::kProfAmp | amc::kProfMom, kPAM = amc::kProfPhase | kAM;
+    if (n == 256) {
+      *used_prof = prof;
+      if (prof == amc::kProfMom)
+        return launch_fusedw<256, CT, amc::kProfMom>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
+      if (prof == kAM) return launch_fusedw<256, CT, kAM>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
+      if (prof == kPAM) return launch_fusedw<256, CT, kPAM>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
+      *used_prof = amc::kProfAll;
+    }
+    if (n == 512 || n == 1024 || n == 2048 || n == 4096) *used_prof = prof;
     switch (n) {
-      case 256: return launch_fusedw<256, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-      case 512: return launch_fused16<512, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-      case 1024: return launch_fused16<1024, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-      case 2048: return launch_fused16<2048, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-      case 4096: return launch_fused16<4096, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-      case 8192: return launch_large<8192, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-      case 16384: return launch_large<16384, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+      case 512: return launch_fused16_profile<512, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
+      case 1024: return launch_fused16_profile<1024, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
+      case 2048: return launch_fused16_profile<2048, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
+      case 4096: return launch_fused16_profile<4096, CT>(prof, iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
       default: break;
     }
   }
   switch (n) {
-    case 256: return launch_fused<256, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-    case 512: return launch_fused<512, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-    case 1024: return launch_fused<1024, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-    case 2048: return launch_fused<2048, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
-    case 4096: return launch_fused<4096, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream);
+    case 256: return launch_fusedw<256, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
+    case 512: return launch_fused16<512, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
+    case 1024: return launch_fused16<1024, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
+    case 2048: return launch_fused16<2048, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
+    case 4096: return launch_fused16<4096, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
+    case 8192: return launch_large<8192, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
+    case 16384: return launch_large<16384, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
     default: return fail(AMC_ERR_UNSUPPORTED, "no fused kernel for frame_size %lld", static_cast<long long>(n));
   }
 }
@@ -372,6 +523,30 @@ bool fused_size(int64_t n) {
 
 constexpr int64_t kGeneralPow2Max = 16384;   // N float2 of FFT scratch must fit in shared memory
 constexpr int64_t kGeneralDftMax = 12288;    // N double2 of twiddles must fit in shared memory
+constexpr size_t kGeneralSmemMax = 200 * 1024;
+
+template <typename CT>
+int general_kernel_attr() {
+  static thread_local bool attr_set[kMaxDevices] = {};
+  int dev = 0;
+  AMC_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {
+    AMC_CUDA(cudaFuncSetAttribute(amc::general_features_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kGeneralSmemMax)));
+    attr_set[dev] = true;
+  }
+  return AMC_OK;
+}
+
+// phase / amplitude cache of 2 N doubles between the passes: aliases the FFT buffer (modes 1, 2) or follows the
+// DFT twiddle table (mode 0); skipped when it does not fit.  Returns the cache offset (-1: none), grows *dyn.
+int place_cache(int64_t n, int fft_mode, size_t* dyn) {
+  const size_t cache = static_cast<size_t>(n) * 2 * sizeof(double);
+  const size_t off = fft_mode == 0 ? *dyn : 0;
+  if (off + cache > kGeneralSmemMax) return -1;
+  if (off + cache > *dyn) *dyn = off + cache;
+  return static_cast<int>(off);
+}
 
 template <typename CT>
 int launch_general(const void* iq, int64_t n_frames, int64_t n, int64_t frame_stride, int64_t sample_stride,
@@ -401,28 +576,44 @@ int launch_general(const void* iq, int64_t n_frames, int64_t n, int64_t frame_st
       dyn = static_cast<size_t>(n) * sizeof(double2);
     }
   }
-  // phase / amplitude cache of 2 N doubles between the passes: aliases the FFT buffer (modes 1, 2) or follows the
-  // DFT twiddle table (mode 0); skipped when it does not fit
-  int cache_off = -1;
-  {
-    const size_t cache = static_cast<size_t>(n) * 2 * sizeof(double);
-    const size_t off = fft_mode == 0 ? dyn : 0;
-    if (off + cache <= 200 * 1024) {
-      cache_off = static_cast<int>(off);
-      if (off + cache > dyn) dyn = off + cache;
-    }
-  }
-  auto kern = amc::general_features_kernel<CT>;
-  AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int cache_off = place_cache(n, fft_mode, &dyn);
+  int rc = general_kernel_attr<CT>();
+  if (rc != AMC_OK) return rc;
   const int64_t cap = static_cast<int64_t>(sms) * 4;
   const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
-  kern<<<grid, amc::kGenThreads, dyn, stream>>>(static_cast<const CT*>(iq), n_frames, static_cast<int>(n),
-                                               frame_stride, sample_stride, out, out_stride, fft_mode, bl.chirp,
-                                               bl.bfft, bl.m, cache_off);
+  amc::general_features_kernel<CT><<<grid, amc::kGenThreads, dyn, stream>>>(
+      static_cast<const CT*>(iq), n_frames, static_cast<int>(n), frame_stride, sample_stride, out, out_stride, fft_mode,
+      bl.chirp, bl.bfft, bl.m, cache_off, 0, 0ull);
   ++t_launches;
   AMC_CUDA(cudaGetLastError());
   return AMC_OK;
 }
+
+// The careful-path pass behind every fused launch: rows the fused kernel tagged (amc_device.cuh: kRedoTagBits) are
+// recomputed by the general kernel; when nothing is tagged - every frame of ordinary data - it only scans column 0
+// of the output (one 8-byte load per frame).  Fused sizes are powers of two <= 16384: float32 radix-2 FFT.
+template <typename CT>
+int launch_redo(const void* iq, int64_t n_frames, int64_t n, int64_t frame_stride, double* out, int64_t out_stride,
+                int sms, cudaStream_t stream, unsigned long long ticket) {
+  size_t dyn = static_cast<size_t>(n) * sizeof(float2);
+  const int cache_off = place_cache(n, 1, &dyn);
+  int rc = general_kernel_attr<CT>();
+  if (rc != AMC_OK) return rc;
+  const int64_t want = (n_frames + 63) / 64;                 // >= 64 rows per CTA: one scan step of 256 threads
+  const int64_t cap = static_cast<int64_t>(sms);             // a light grid: it normally exits at once
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  AMC_CUDA(launch_pdl(amc::general_features_kernel<CT>, grid, amc::kGenThreads, dyn, stream, static_cast<const CT*>(iq),
+                      n_frames, static_cast<int>(n), frame_stride, 1, out, out_stride, 1, nullptr, nullptr, 0, cache_off, 1,
+                      ticket));
+  ++t_launches;
+  return AMC_OK;
+}
+
+#ifdef AMC_EXPERIMENTS
+constexpr int kKnownFlags = AMC_FLAG_FORCE_GENERAL | AMC_FLAG_DIRECT_DFT | AMC_FLAG_FUSED_SPT8 | AMC_FLAG_FUSED_WS;
+#else
+constexpr int kKnownFlags = AMC_FLAG_FORCE_GENERAL | AMC_FLAG_DIRECT_DFT;
+#endif
 
 int check_common(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size, int64_t frame_stride,
                  int64_t sample_stride) {
@@ -436,61 +627,114 @@ int check_common(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_s
   return AMC_OK;
 }
 
-// ---------------------------------------------------------------- host pipeline state (per device)
+// ---------------------------------------------------------------- host pipeline state (a small pool per device)
+// One pipe = two streams + double-buffered device / pinned staging buffers.  Concurrent host calls on the same device
+// each take their own pipe (up to kMaxPipes, then they queue), so one long call does not serialise the others.
 struct HostPipe {
+  bool busy = false;
   bool ready = false;
   cudaStream_t stream[2] = {nullptr, nullptr};
   void* d_in[2] = {nullptr, nullptr};
   void* d_tr[2] = {nullptr, nullptr};   // transposed copy for sample-major input
   double* d_out[2] = {nullptr, nullptr};
-  size_t in_bytes = 0, tr_bytes = 0, out_bytes = 0;
+  size_t in_bytes[2] = {0, 0}, tr_bytes[2] = {0, 0}, out_bytes[2] = {0, 0};
   // pageable sources (numpy arrays, memory-mapped .mat planes): gathered by a few host threads into these pinned
   // buffers and copied from there - a cudaMemcpy2DAsync from pageable memory is staged by the driver on ONE thread
   void* h_in[2] = {nullptr, nullptr};
+  size_t h_bytes[2] = {0, 0};
   cudaEvent_t h2d_done[2] = {nullptr, nullptr};
-  size_t h_bytes = 0;
 };
-HostPipe g_pipe[kMaxDevices];
+constexpr int kMaxPipes = 4;
+HostPipe g_pipe[kMaxDevices][kMaxPipes];
 std::mutex g_pipe_mu[kMaxDevices];
+std::condition_variable g_pipe_cv[kMaxDevices];
 
-int ensure_pipe(HostPipe& p, size_t in_bytes, size_t tr_bytes, size_t out_bytes) {
-  if (!p.ready) {
-    for (int i = 0; i < 2; ++i) AMC_CUDA(cudaStreamCreateWithFlags(&p.stream[i], cudaStreamNonBlocking));
-    p.ready = true;
-  }
-  for (int i = 0; i < 2; ++i) {
-    if (p.in_bytes < in_bytes) {
-      if (p.d_in[i]) AMC_CUDA(cudaFree(p.d_in[i]));
-      p.d_in[i] = nullptr;
-      AMC_CUDA(cudaMalloc(&p.d_in[i], in_bytes));
-    }
-    if (p.tr_bytes < tr_bytes) {
-      if (p.d_tr[i]) AMC_CUDA(cudaFree(p.d_tr[i]));
-      p.d_tr[i] = nullptr;
-      AMC_CUDA(cudaMalloc(&p.d_tr[i], tr_bytes));
-    }
-    if (p.out_bytes < out_bytes) {
-      if (p.d_out[i]) AMC_CUDA(cudaFree(p.d_out[i]));
-      p.d_out[i] = nullptr;
-      AMC_CUDA(cudaMalloc(reinterpret_cast<void**>(&p.d_out[i]), out_bytes));
+struct PipeLease {
+  int device = -1;
+  HostPipe* pipe = nullptr;
+  ~PipeLease() {
+    if (pipe) {
+      {
+        std::lock_guard<std::mutex> lk(g_pipe_mu[device]);
+        pipe->busy = false;
+      }
+      g_pipe_cv[device].notify_one();
     }
   }
-  if (p.in_bytes < in_bytes) p.in_bytes = in_bytes;
-  if (p.tr_bytes < tr_bytes) p.tr_bytes = tr_bytes;
-  if (p.out_bytes < out_bytes) p.out_bytes = out_bytes;
+};
+void acquire_pipe(int device, PipeLease* lease) {
+  std::unique_lock<std::mutex> lk(g_pipe_mu[device]);
+  for (;;) {
+    for (int i = 0; i < kMaxPipes; ++i) {
+      if (!g_pipe[device][i].busy) {
+        g_pipe[device][i].busy = true;
+        lease->device = device;
+        lease->pipe = &g_pipe[device][i];
+        return;
+      }
+    }
+    g_pipe_cv[device].wait(lk);
+  }
+}
+
+// grow one buffer; its recorded size is valid only while the pointer is (a failed allocation leaves {nullptr, 0})
+template <typename Alloc, typename Free>
+int grow(void** ptr, size_t* have, size_t want, Alloc alloc, Free release, const char* what) {
+  if (*have >= want) return AMC_OK;
+  if (*ptr) {
+    void* old = *ptr;
+    *ptr = nullptr;
+    *have = 0;
+    const cudaError_t e = release(old);
+    if (e != cudaSuccess) return fail(AMC_ERR_CUDA, "freeing the %s buffer failed: %s", what, cudaGetErrorString(e));
+  }
+  const cudaError_t e = alloc(ptr, want);
+  if (e != cudaSuccess) {
+    *ptr = nullptr;
+    *have = 0;
+    cudaGetLastError();
+    return fail(AMC_ERR_CUDA, "allocating %zu bytes for the %s buffer failed: %s", want, what, cudaGetErrorString(e));
+  }
+  *have = want;
   return AMC_OK;
 }
 
+int ensure_pipe(HostPipe& p, size_t in_bytes, size_t tr_bytes, size_t out_bytes) {
+  if (!p.ready) {
+    for (int i = 0; i < 2; ++i)
+      if (!p.stream[i]) AMC_CUDA(cudaStreamCreateWithFlags(&p.stream[i], cudaStreamNonBlocking));
+    p.ready = true;
+  }
+  auto dev_alloc = [](void** q, size_t n) { return cudaMalloc(q, n); };
+  auto dev_free = [](void* q) { return cudaFree(q); };
+  for (int i = 0; i < 2; ++i) {
+    int rc = grow(&p.d_in[i], &p.in_bytes[i], in_bytes, dev_alloc, dev_free, "device input");
+    if (rc == AMC_OK) rc = grow(&p.d_tr[i], &p.tr_bytes[i], tr_bytes, dev_alloc, dev_free, "device re-layout");
+    if (rc == AMC_OK)
+      rc = grow(reinterpret_cast<void**>(&p.d_out[i]), &p.out_bytes[i], out_bytes, dev_alloc, dev_free, "device output");
+    if (rc != AMC_OK) return rc;
+  }
+  return AMC_OK;
+}
+
+// AMCPY_B200_STAGING_WC=1: write-combined pinned staging (the host threads only ever write it)
+bool staging_write_combined() {
+  static const bool wc = [] {
+    const char* env = std::getenv("AMCPY_B200_STAGING_WC");
+    return env && *env && std::atoi(env) != 0;
+  }();
+  return wc;
+}
+
 int ensure_pinned_staging(HostPipe& p, size_t bytes) {
+  const unsigned flags = staging_write_combined() ? cudaHostAllocWriteCombined : cudaHostAllocDefault;
+  auto host_alloc = [flags](void** q, size_t n) { return cudaHostAlloc(q, n, flags); };
+  auto host_free = [](void* q) { return cudaFreeHost(q); };
   for (int i = 0; i < 2; ++i) {
     if (!p.h2d_done[i]) AMC_CUDA(cudaEventCreateWithFlags(&p.h2d_done[i], cudaEventDisableTiming));
-    if (p.h_bytes < bytes) {
-      if (p.h_in[i]) AMC_CUDA(cudaFreeHost(p.h_in[i]));
-      p.h_in[i] = nullptr;
-      AMC_CUDA(cudaMallocHost(&p.h_in[i], bytes));
-    }
+    const int rc = grow(&p.h_in[i], &p.h_bytes[i], bytes, host_alloc, host_free, "pinned staging");
+    if (rc != AMC_OK) return rc;
   }
-  if (p.h_bytes < bytes) p.h_bytes = bytes;
   return AMC_OK;
 }
 
@@ -564,7 +808,7 @@ void gather_rows(unsigned char* dst, size_t dst_pitch, const unsigned char* src,
 
 extern "C" {
 
-int amc_version(void) { return 1000; }
+int amc_version(void) { return 2000; }
 
 const char* amc_last_error_string(void) { return t_err.c_str(); }
 
@@ -580,11 +824,55 @@ int amc_device_count(void) {
   return n;
 }
 
+int amc_init(int device) {
+  if (device < 0 || device >= kMaxDevices) return fail(AMC_ERR_INVALID_ARG, "device %d out of range", device);
+  DeviceGuard guard;
+  AMC_CUDA(cudaGetDevice(&guard.prev));
+  AMC_CUDA(cudaSetDevice(device));
+  guard.armed = true;
+  DevInfo di;
+  int rc = device_info(&di);
+  if (rc != AMC_OK) return rc;
+  cudaStream_t init_stream;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    rc = init_stream_locked(g_dev[device]);
+    if (rc != AMC_OK) return rc;
+    init_stream = g_dev[device].init_stream;
+  }
+  rc = ensure_twiddles(device, init_stream);
+  if (rc != AMC_OK) return rc;
+  AMC_CUDA(cudaStreamSynchronize(init_stream));
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_dev[device].tw_done = true;
+  return AMC_OK;
+}
+
+int64_t amc_workspace_bytes(int iq_dtype, int64_t n_frames, int64_t frame_size, int host_path) {
+  if (iq_dtype != AMC_C64 && iq_dtype != AMC_C128) return fail(AMC_ERR_INVALID_ARG, "iq_dtype %d unknown", iq_dtype);
+  if (n_frames < 0 || frame_size < 1) return fail(AMC_ERR_INVALID_ARG, "bad shape");
+  int64_t bytes = 0;
+  if (!is_pow2(frame_size)) {                       // Bluestein tables, cached per (device, frame_size)
+    const int64_t m = bluestein_m(frame_size);
+    if (m > 0) bytes += (frame_size + m) * static_cast<int64_t>(sizeof(float2));
+  }
+  if (host_path) {                                  // double-buffered chunk buffers of one pipe
+    const int64_t elt = iq_dtype == AMC_C128 ? 16 : 8;
+    const int64_t frame_bytes = frame_size * elt;
+    int64_t chunk = (64ll << 20) / frame_bytes;
+    chunk = chunk < 32 ? 32 : (chunk / 32) * 32;
+    if (chunk > n_frames) chunk = n_frames;
+    bytes += 2 * (2 * chunk * frame_bytes + chunk * AMC_N_FEATURES * static_cast<int64_t>(sizeof(double)));
+  }
+  return bytes;
+}
+
 int amc_extract_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t frame_size, int64_t frame_stride,
                       int64_t sample_stride, double* out, int64_t out_stride, uint32_t feature_mask, int flags,
                       void* cuda_stream) {
   int rc = check_common(iq, iq_dtype, n_frames, frame_size, frame_stride, sample_stride);
   if (rc != AMC_OK) return rc;
+  if (flags & ~kKnownFlags) return fail(AMC_ERR_INVALID_ARG, "unknown flag bits 0x%x", flags & ~kKnownFlags);
   if ((feature_mask & AMC_ALL_FEATURES) == 0) return fail(AMC_ERR_INVALID_ARG, "feature_mask selects nothing");
   if (out_stride < AMC_N_FEATURES) return fail(AMC_ERR_INVALID_ARG, "out_stride %lld < 18", (long long)out_stride);
   if (n_frames == 0) return AMC_OK;
@@ -601,14 +889,21 @@ int amc_extract_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t fr
   if (fused) {
     rc = ensure_twiddles(di.dev, stream);
     if (rc != AMC_OK) return rc;
-    const bool spt8 = (flags & AMC_FLAG_FUSED_SPT8) != 0;
-    const bool ws = (flags & AMC_FLAG_FUSED_WS) != 0;
     const int prof = pick_profile(feature_mask);
+    int used = amc::kProfAll;
+    const unsigned long long ticket = g_ticket.fetch_add(1, std::memory_order_relaxed);
     if (iq_dtype == AMC_C128)
-      return dispatch_fused<double2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, spt8, ws,
-                                     prof);
-    return dispatch_fused<float2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, spt8, ws,
-                                  prof);
+      rc = dispatch_fused<double2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, flags, prof,
+                                   &used, ticket);
+    else
+      rc = dispatch_fused<float2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, flags, prof,
+                                  &used, ticket);
+    if (rc != AMC_OK) return rc;
+    if (used == amc::kProfMom) return AMC_OK;        // float64 sums only: nothing for the careful path to redo
+    const unsigned long long tk = used < 0 ? 0ull : ticket;   // 0: always scan (A/B experiment kernels)
+    if (iq_dtype == AMC_C128)
+      return launch_redo<double2>(iq, n_frames, frame_size, frame_stride, out, out_stride, di.sms, stream, tk);
+    return launch_redo<float2>(iq, n_frames, frame_size, frame_stride, out, out_stride, di.sms, stream, tk);
   }
   if (iq_dtype == AMC_C128)
     return launch_general<double2>(iq, n_frames, frame_size, frame_stride, sample_stride, out, out_stride, di.sms,
@@ -729,9 +1024,10 @@ int amc_extract_host(const void* iq, int iq_dtype, int64_t n_frames, int64_t fra
     return fail(AMC_ERR_UNSUPPORTED,
                 "host layout must be row-per-frame (sample_stride 1) or sample-major (frame_stride 1)");
   if (device < 0 || device >= kMaxDevices) return fail(AMC_ERR_INVALID_ARG, "device %d out of range", device);
-  int prev = 0;
-  AMC_CUDA(cudaGetDevice(&prev));
+  DeviceGuard guard;                                 // restores the caller's device on every exit path
+  AMC_CUDA(cudaGetDevice(&guard.prev));
   AMC_CUDA(cudaSetDevice(device));
+  guard.armed = true;
 
   const size_t elt = iq_dtype == AMC_C128 ? 16 : 8;
   const size_t frame_bytes = static_cast<size_t>(frame_size) * elt;
@@ -740,22 +1036,17 @@ int amc_extract_host(const void* iq, int iq_dtype, int64_t n_frames, int64_t fra
   chunk = chunk < 32 ? 32 : (chunk / 32) * 32;
   if (chunk > n_frames) chunk = n_frames;
 
-  std::lock_guard<std::mutex> lk(g_pipe_mu[device]);
-  HostPipe& p = g_pipe[device];
+  PipeLease lease;                                   // this call's own streams + staging buffers
+  acquire_pipe(device, &lease);
+  HostPipe& p = *lease.pipe;
   rc = ensure_pipe(p, static_cast<size_t>(chunk) * frame_bytes, sample_major ? static_cast<size_t>(chunk) * frame_bytes : 0,
                    static_cast<size_t>(chunk) * AMC_N_FEATURES * sizeof(double));
-  if (rc != AMC_OK) {
-    cudaSetDevice(prev);
-    return rc;
-  }
+  if (rc != AMC_OK) return rc;
   const unsigned char* src = static_cast<const unsigned char*>(iq);
   const bool staged = is_pageable_host(iq) && static_cast<size_t>(n_frames) * frame_bytes >= (8u << 20);
   if (staged) {
     rc = ensure_pinned_staging(p, static_cast<size_t>(chunk) * frame_bytes);
-    if (rc != AMC_OK) {
-      cudaSetDevice(prev);
-      return rc;
-    }
+    if (rc != AMC_OK) return rc;
   }
   int status = AMC_OK;
   int64_t c = 0;
@@ -817,7 +1108,6 @@ int amc_extract_host(const void* iq, int iq_dtype, int64_t n_frames, int64_t fra
     if (e != cudaSuccess && status == AMC_OK)
       status = fail(AMC_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
   }
-  cudaSetDevice(prev);
   return status;
 }
 
@@ -833,9 +1123,10 @@ int amc_extract_host_planar(const void* re, const void* im, int iq_dtype, int64_
   if (sample_stride < n_frames) return fail(AMC_ERR_INVALID_ARG, "sample_stride < n_frames");
   if (frame_size > 65535LL * 32) return fail(AMC_ERR_UNSUPPORTED, "frame_size too large for the re-layout grid");
   if (device < 0 || device >= kMaxDevices) return fail(AMC_ERR_INVALID_ARG, "device %d out of range", device);
-  int prev = 0;
-  AMC_CUDA(cudaGetDevice(&prev));
+  DeviceGuard guard;                                 // restores the caller's device on every exit path
+  AMC_CUDA(cudaGetDevice(&guard.prev));
   AMC_CUDA(cudaSetDevice(device));
+  guard.armed = true;
 
   const size_t relt = iq_dtype == AMC_C128 ? 8 : 4;            // bytes per real plane element
   const size_t frame_bytes = static_cast<size_t>(frame_size) * 2 * relt;
@@ -843,23 +1134,18 @@ int amc_extract_host_planar(const void* re, const void* im, int iq_dtype, int64_
   chunk = chunk < 32 ? 32 : (chunk / 32) * 32;
   if (chunk > n_frames) chunk = n_frames;
 
-  std::lock_guard<std::mutex> lk(g_pipe_mu[device]);
-  HostPipe& p = g_pipe[device];
+  PipeLease lease;                                   // this call's own streams + staging buffers
+  acquire_pipe(device, &lease);
+  HostPipe& p = *lease.pipe;
   rc = ensure_pipe(p, static_cast<size_t>(chunk) * frame_bytes, static_cast<size_t>(chunk) * frame_bytes,
                    static_cast<size_t>(chunk) * AMC_N_FEATURES * sizeof(double));
-  if (rc != AMC_OK) {
-    cudaSetDevice(prev);
-    return rc;
-  }
+  if (rc != AMC_OK) return rc;
   const unsigned char* src_re = static_cast<const unsigned char*>(re);
   const unsigned char* src_im = static_cast<const unsigned char*>(im);
   const bool staged = is_pageable_host(re) && static_cast<size_t>(n_frames) * frame_bytes >= (8u << 20);
   if (staged) {
     rc = ensure_pinned_staging(p, static_cast<size_t>(chunk) * frame_bytes);
-    if (rc != AMC_OK) {
-      cudaSetDevice(prev);
-      return rc;
-    }
+    if (rc != AMC_OK) return rc;
   }
   int status = AMC_OK;
   int64_t c = 0;
@@ -921,7 +1207,6 @@ int amc_extract_host_planar(const void* re, const void* im, int iq_dtype, int64_
     if (e != cudaSuccess && status == AMC_OK)
       status = fail(AMC_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
   }
-  cudaSetDevice(prev);
   return status;
 }
 

@@ -280,6 +280,7 @@ struct FrameSums {
   double mono[15];   // sums of a^p b^q
   double sum_r;      // sum |x|
   double c_abs1;     // sum |r - mean r|
+  double c_abs2;     // sum (|cn| - mean |cn|)^2, cn = r / mean r - 1   (careful path only: general kernel, third pass)
   double c2, c4;     // sum (r-mean)^2, ^4
   double ph_m2;      // sum (phi - mean)^2
   double aph_m2;     // sum (|phi| - mean)^2
@@ -288,18 +289,76 @@ struct FrameSums {
   double spec_max;   // max_k |X_k|^2
 };
 
+// ------------------------------------------------------------------ fast path -> careful path hand-over
+// The fused kernels compute the spectrum and the phases in FLOAT32 and feature 4 from a one-pass formula.  That is
+// inside the 1e-6 / 1e-9 classes for every frame except a few well-defined kinds, which finalize_features detects
+// from the frame's sums and hands to the general (float64, scaled-FFT, three-pass) kernel by writing this tag into
+// column 0 of the frame's row: the library launches `general_features_kernel` in redo mode right after every fused
+// kernel; it scans column 0 and recomputes exactly the tagged rows (amc_api.cu: launch_redo).
+//   kCheckRange : mean power outside [2^-100, 2^80 * 2048/N]: float32 squares would under/overflow (features 1,2,3,5,9)
+//   kCheckPhase : phase / |phase| / frequency spread below kNarrowRad: the float32 phases carry ~1e-7 rad of rounding
+//                 noise, i.e. ~3e-8/sigma relative on features 2, 3, 5, 9 (unmodulated carrier, dominant DC line)
+//   kCheckAmp   : spread of |r - mean r| below 0.3 % of its mean: sum d^2 - (sum|d|)^2/N cancels (feature 4;
+//                 two-level amplitudes at very high SNR, 2-sample frames)
+// A quiet NaN with a payload no arithmetic produces; NaN input frames keep the ordinary NaN.
+constexpr unsigned long long kRedoTagBits = 0x7ff8b200a3c10001ULL;
+// "Did launch `ticket` tag anything?"  Every fused launch carries a unique, increasing ticket; tagging a row raises
+// slot ticket % 256 to the ticket (atomicMax: the slots only ever grow, nothing is reset, launches on different
+// streams cannot erase each other's mark).  The careful-path launch that follows returns at once while its slot is
+// still below its ticket - the case for every batch of ordinary frames - and scans the rows otherwise (a slot shared
+// with a later launch can only cause a superfluous scan, never a missed one).
+__device__ unsigned long long g_redo_ring[256];
+// Programmatic dependent launch: the careful-path kernel is launched while the fused kernel is still running and
+// parks here until that grid has completed and its writes are visible (no-ops for ordinary launches).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+constexpr int kCheckRange = 1, kCheckPhase = 2, kCheckAmp = 4;
+constexpr int kCheckAll = 7;
+constexpr double kNarrowRad = 0.1;          // rad; below it the careful path takes over
+
 // Writes the 18 features (column k = feature id k+1, features.py:192-211).
-__device__ __noinline__ void finalize_features(const FrameSums& fs, int n, double* __restrict__ out) {
+// `checks` (kCheck*): which fast-path validity tests apply to the kernel that produced `fs`; 0 = the sums are
+// float64-grade already (general kernel).  Returns true when the row was tagged for the careful path instead.
+__device__ __noinline__ bool finalize_features(const FrameSums& fs, int n, double* __restrict__ out, int checks,
+                                               unsigned long long ticket = 0) {
   const double dn = static_cast<double>(n);
   const double inv_n = 1.0 / dn;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  const double pw = (fs.mono[0] + fs.mono[1]) * inv_n;               // mean |x|^2
+  if (checks != 0 && n >= 2 && pw == pw) {                           // (NaN frames stay on the NaN rule below)
+    bool redo = false;
+    if (checks & kCheckRange) {
+      const double hi = 1.2089258196146292e+24 * (2048.0 * inv_n);   // 2^80 * 2048/N: N^2 * sum|x|^2 stays < 2^126
+      redo = redo || !(pw >= 7.888609052210118e-31 && pw <= hi);     // 2^-100; also catches +inf and an all-zero frame
+    }
+    if (checks & kCheckPhase) {
+      const double thr = kNarrowRad * kNarrowRad;
+      constexpr double k4pi2 = 39.47841760435743;                    // f_m2 is in cycles^2
+      redo = redo || fs.ph_m2 < thr * (dn - 1.0) || fs.aph_m2 < thr * (dn - 1.0) ||
+             (n >= 3 && fs.f_m2 * k4pi2 < thr * (dn - 2.0));
+    }
+    if (checks & kCheckAmp) {
+      redo = redo || (fs.c2 - fs.c_abs1 * fs.c_abs1 * inv_n) < 1.0e-5 * fs.c2;
+    }
+    if (redo) {
+      if (ticket != 0) atomicMax(&g_redo_ring[ticket & 255], ticket);
+      out[0] = __longlong_as_double(static_cast<long long>(kRedoTagBits));
+#pragma unroll
+      for (int i = 1; i < 18; ++i) out[i] = nan;
+      return true;
+    }
+  }
   out[0] = fs.spec_max / dn;                                         // features.py:68-69
   out[1] = sqrt(fs.aph_m2 / (dn - 1.0));                             // :74
   out[2] = sqrt(fs.ph_m2 / (dn - 1.0));                              // :79
   const double mu = fs.sum_r * inv_n;
-  // std(|r/mu - 1|, ddof=1) = sqrt((sum d^2 - (sum|d|)^2/N)/(N-1)) / mu, d = r - mu    (:82-85)
-  const double v4 = (fs.c2 - fs.c_abs1 * fs.c_abs1 * inv_n) / (dn - 1.0);
-  out[3] = sqrt(fmax(v4, 0.0)) / mu;
+  if (checks == 0) {
+    out[3] = sqrt(fs.c_abs2 / (dn - 1.0));                           // careful path: np.std's two passes over |cn_amplitude|
+  } else {
+    // std(|r/mu - 1|, ddof=1) = sqrt((sum d^2 - (sum|d|)^2/N)/(N-1)) / mu, d = r - mu    (:82-85)
+    const double v4 = (fs.c2 - fs.c_abs1 * fs.c_abs1 * inv_n) / (dn - 1.0);
+    out[3] = sqrt(fmax(v4, 0.0)) / mu;
+  }
   out[4] = sqrt(fs.f_m2 / (dn - 2.0));                               // :88-91 (N-1 values, ddof=1)
   out[5] = mu;                                                       // :96
   out[6] = sqrt(fs.sum_r) / dn;                                      // :101
@@ -359,6 +418,7 @@ __device__ __noinline__ void finalize_features(const FrameSums& fs, int n, doubl
 #pragma unroll
     for (int i = 0; i < 18; ++i) out[i] = nan;
   }
+  return false;
 }
 
 // columns of the feature groups a reduced profile did not compute

@@ -1,6 +1,8 @@
-// Fused sm_100a kernel, first generation (8 samples per thread): all 18 features of a frame from
-// ONE read of the frame out of HBM.  Superseded by amc_fused16.cuh / amc_fusedw.cuh / amc_large.cuh
-// (which reuse the building blocks defined here) and kept behind AMC_FLAG_FUSED_SPT8 for A/B runs.
+// Building blocks shared by the fused sm_100a kernels (amc_fused16.cuh / amc_fusedw.cuh / amc_large.cuh): small FP32
+// DFTs, twiddle tables of the radix-8 stages, sample loads, the FP64 tie re-decision, group barriers.
+//
+// With -DAMC_EXPERIMENTS the file also compiles the round-1 first-generation kernel (8 samples per thread,
+// AMC_FLAG_FUSED_SPT8) for A/B runs; it is NOT part of the product library:
 //
 //   * persistent CTAs; each "group" of N/8 threads owns one frame at a time (N=2048: 256 threads
 //     = the whole CTA; N=256: one warp per frame, 8 frames per CTA);
@@ -100,6 +102,7 @@ __device__ __noinline__ float exact_phase_step(const CT* xs, int n) {
   return static_cast<float>(unwrap_step(p1 - p0));
 }
 
+#ifdef AMC_EXPERIMENTS
 template <int N, typename CT>
 struct FusedCfg {
   static constexpr int SPT = 8;                         // samples per thread
@@ -120,6 +123,8 @@ struct FusedCfg {
   static_assert(GROUP % 32 == 0 && GROUP >= 32 && GROUP <= 1024, "frame size outside fused range");
   static_assert(GROUP_BYTES % 16 == 0, "group region must keep 16-byte alignment");
 };
+
+#endif  // AMC_EXPERIMENTS
 
 template <int GROUP, int CTA>
 __device__ __forceinline__ void group_sync(int g) {
@@ -161,6 +166,8 @@ __device__ __noinline__ float exact_freq_step(const CT* xs, int n) {
   const double p1 = atan2_exact(static_cast<double>(v1.y), static_cast<double>(v1.x));
   return static_cast<float>(unwrap_step(p1 - p0) / kTwoPi);
 }
+
+#ifdef AMC_EXPERIMENTS
 
 template <int N, typename CT>
 __global__ void __launch_bounds__(FusedCfg<N, CT>::CTA, FusedCfg<N, CT>::MIN_BLOCKS)
@@ -449,7 +456,7 @@ fused_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
       fs.mean_f = static_cast<double>(totf[2]) / (N - 1);
       fs.spec_max = static_cast<double>(mx);
       double res[18];
-      finalize_features(fs, N, res);
+      finalize_features(fs, N, res, kCheckAll);
       if (lane < 18) {
         double val = res[0];
 #pragma unroll
@@ -459,5 +466,7 @@ fused_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     }
   }
 }
+
+#endif  // AMC_EXPERIMENTS
 
 }  // namespace amc

@@ -88,8 +88,33 @@ __device__ float2 g_tw_a[15 * (32 + 64 + 128 + 256)];
 __device__ float2 g_tw_b[15 * (2 + 4 + 8 + 16)];
 __host__ __device__ constexpr int tw_a_offset(int n) { return 15 * (n == 512 ? 0 : (n == 1024 ? 32 : (n == 2048 ? 96 : 224))); }
 __host__ __device__ constexpr int tw_b_offset(int n) { return 15 * (n == 512 ? 0 : (n == 1024 ? 2 : (n == 2048 ? 6 : 14))); }
+// The same twiddles in PAIRS, one 16-byte load for two of them (8 loads per stage instead of 15):
+//   g_tw_a4[off_a4(N)][p][t]  = {W_N^(t (2p+1)), W_N^(t (2p+2))}            p = 0..7 (the second half of p = 7 is unused)
+//   g_tw_b4[off_b4(N)][p][m1] = {W_(N/16)^(m1 (2p+1)), W_(N/16)^(m1 (2p+2))}
+__device__ float4 g_tw_a4[8 * (32 + 64 + 128 + 256)];
+__device__ float4 g_tw_b4[8 * (2 + 4 + 8 + 16)];
+__host__ __device__ constexpr int tw_a4_offset(int n) { return 8 * (n == 512 ? 0 : (n == 1024 ? 32 : (n == 2048 ? 96 : 224))); }
+__host__ __device__ constexpr int tw_b4_offset(int n) { return 8 * (n == 512 ? 0 : (n == 1024 ? 2 : (n == 2048 ? 6 : 14))); }
 __global__ void init_twiddle16dif_kernel() {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 8 * 480) {
+    int n = 512, rel = i;
+    while (rel >= 8 * (n / 16)) { rel -= 8 * (n / 16); n *= 2; }
+    const int grp = n / 16, p = rel / grp, t = rel % grp;
+    double s0, c0, s1, c1;
+    sincospi(-2.0 * static_cast<double>(t * (2 * p + 1)) / static_cast<double>(n), &s0, &c0);
+    sincospi(-2.0 * static_cast<double>(t * (2 * p + 2)) / static_cast<double>(n), &s1, &c1);
+    g_tw_a4[i] = make_float4(static_cast<float>(c0), static_cast<float>(s0), static_cast<float>(c1), static_cast<float>(s1));
+  }
+  if (i < 8 * 30) {
+    int n = 512, rel = i;
+    while (rel >= 8 * (n / 256)) { rel -= 8 * (n / 256); n *= 2; }
+    const int m1n = n / 256, p = rel / m1n, m1 = rel % m1n;
+    double s0, c0, s1, c1;
+    sincospi(-2.0 * static_cast<double>(m1 * (2 * p + 1)) / static_cast<double>(n / 16), &s0, &c0);
+    sincospi(-2.0 * static_cast<double>(m1 * (2 * p + 2)) / static_cast<double>(n / 16), &s1, &c1);
+    g_tw_b4[i] = make_float4(static_cast<float>(c0), static_cast<float>(s0), static_cast<float>(c1), static_cast<float>(s1));
+  }
   if (i < 15 * 480) {
     int n = 512, rel = i;
     while (rel >= 15 * (n / 16)) { rel -= 15 * (n / 16); n *= 2; }
@@ -154,7 +179,8 @@ struct Fused16Cfg {
 template <int N, typename CT, int PROF = kProfAll>
 __global__ void __launch_bounds__(Fused16Cfg<N, CT>::CTA, Fused16Cfg<N, CT>::MIN_BLOCKS)
 fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame_stride,
-                        double* __restrict__ out, int64_t out_stride) {
+                        double* __restrict__ out, int64_t out_stride, unsigned long long ticket) {
+  pdl_launch_dependents();   // the careful-path kernel may be launched now; it waits for this grid to complete
   using Cfg = Fused16Cfg<N, CT>;
   constexpr int GROUP = Cfg::GROUP, W = Cfg::W, SPT = Cfg::SPT, M1 = Cfg::M1, LOG_M1 = Cfg::LOG_M1;
   constexpr bool DO_FFT = (PROF & kProfFft) != 0, DO_PHASE = (PROF & kProfPhase) != 0, DO_AMP = (PROF & kProfAmp) != 0,
@@ -192,6 +218,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait_primary();                 // the predecessor in the stream has completed: global memory may be touched
   if (lane == 0) mbar_arrive(rbar);   // phase 0 = "nothing to wait for" (keeps the wait in the loop unconditional)
   if (t == 0 && my_frames > 0) {
     mbar_arrive_expect_tx(bar, Cfg::SLOT_BYTES);
@@ -241,8 +268,9 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         fs.spec_max = pl[24];
         const int64_t fo = gg + static_cast<int64_t>(k - bi + lane) * tg;
         double* row = out + fo * out_stride;
-        finalize_features(fs, N, row);
-        blank_skipped_groups<PROF>(row);
+        constexpr int kChecks = ((DO_FFT || DO_PHASE) ? kCheckRange : 0) | (DO_PHASE ? kCheckPhase : 0) |
+                                (DO_AMP ? kCheckAmp : 0);
+        if (!finalize_features(fs, N, row, kChecks, ticket)) blank_skipped_groups<PROF>(row);
       }
       __syncwarp();
     }
@@ -392,11 +420,22 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       for (int q = 0; q < 16; ++q) v[q] = make_float2(xr[q], xi[q]);
 #endif
       dft16(v);
+#ifdef AMC_TW_V2
       float2 tw[15];
 #pragma unroll
       for (int q = 1; q < 16; ++q) tw[q - 1] = g_tw_a[tw_a_offset(N) + (q - 1) * GROUP + tv];   // 256 B per warp load
 #pragma unroll
       for (int q = 1; q < 16; ++q) v[bitrev4(q)] = c_mul(v[bitrev4(q)], tw[q - 1]);
+#else
+      float4 tw[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) tw[p] = g_tw_a4[tw_a4_offset(N) + p * GROUP + tv];            // 512 B per warp load
+#pragma unroll
+      for (int q = 1; q < 16; ++q) {
+        const float4 w = tw[(q - 1) >> 1];
+        v[bitrev4(q)] = c_mul(v[bitrev4(q)], (q & 1) ? make_float2(w.x, w.y) : make_float2(w.z, w.w));
+      }
+#endif
 #pragma unroll
       for (int q = 0; q < 16; ++q) {   // element (t, q) -> row t, slot q ^ rot_t
         const float2 o = v[bitrev4(q)];
@@ -477,17 +516,31 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       const int k1b = wv * Cfg::F + (lv >> LOG_M1);                  // sub-transform of this lane in stage B
       const int kk_b = k1b ^ ((m1 << (4 - LOG_M1)) & 15);
       float2* wr_t = tb + lv * kTRow;
+#ifdef AMC_TW_V2
       float2 tw[15];
 #pragma unroll
       for (int q = 1; q < 16; ++q) tw[q - 1] = g_tw_b[tw_b_offset(N) + (q - 1) * M1 + m1];
+#else
+      float4 tw[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) tw[p] = g_tw_b4[tw_b4_offset(N) + p * M1 + m1];
+#endif
 #pragma unroll
       for (int m2 = 0; m2 < 16; ++m2) {
         // (n1 & 15) = m1 + M1 (m2 mod 16/M1): the rotated swizzle is base ^ (m2 mod 16/M1)
         v[m2] = buf_a[m1 * 16 + (kk_b ^ (m2 & (16 / M1 - 1))) + 16 * M1 * m2];
       }
       dft16(v);
+#ifdef AMC_TW_V2
 #pragma unroll
       for (int q = 1; q < 16; ++q) v[bitrev4(q)] = c_mul(v[bitrev4(q)], tw[q - 1]);
+#else
+#pragma unroll
+      for (int q = 1; q < 16; ++q) {
+        const float4 w = tw[(q - 1) >> 1];
+        v[bitrev4(q)] = c_mul(v[bitrev4(q)], (q & 1) ? make_float2(w.x, w.y) : make_float2(w.z, w.w));
+      }
+#endif
 #pragma unroll
       for (int q = 0; q < 16; ++q) wr_t[q] = v[bitrev4(q)];
     }

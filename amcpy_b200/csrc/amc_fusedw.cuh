@@ -33,7 +33,8 @@ struct FusedWCfg {
 template <int N, typename CT, int PROF = kProfAll>
 __global__ void __launch_bounds__(FusedWCfg<N, CT>::CTA, FusedWCfg<N, CT>::MIN_BLOCKS)
 fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame_stride,
-                       double* __restrict__ out, int64_t out_stride) {
+                       double* __restrict__ out, int64_t out_stride, unsigned long long ticket) {
+  pdl_launch_dependents();   // the careful-path kernel may be launched now; it waits for this grid to complete
   using Cfg = FusedWCfg<N, CT>;
   constexpr int SPT = Cfg::SPT;
   // feature groups of this instantiation (feature_mask profiles, see amc_device.cuh: kProf*)
@@ -64,6 +65,7 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait_primary();          // the predecessor in the stream has completed: global memory may be touched
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < 2; ++s)
@@ -278,8 +280,9 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
         fs.mean_f = pl[23] / (N - 1);
         fs.spec_max = pl[24];
         const int64_t fo = gg + static_cast<int64_t>(it - bi + lane) * tg;
-        finalize_features(fs, N, out + fo * out_stride);
-        blank_skipped_groups<PROF>(out + fo * out_stride);
+        constexpr int kChecks = ((DO_FFT || DO_PHASE) ? kCheckRange : 0) | (DO_PHASE ? kCheckPhase : 0) |
+                                (DO_AMP ? kCheckAmp : 0);
+        if (!finalize_features(fs, N, out + fo * out_stride, kChecks, ticket)) blank_skipped_groups<PROF>(out + fo * out_stride);
       }
       __syncwarp();
     }

@@ -97,19 +97,260 @@ __device__ __forceinline__ void smem_ifft_dit(float2* buf, int m, int tid) {
 //               pow2 >= 2N-1, FFT, times the pre-transformed conjugate chirp `bl_bfft` (bit-reversed order, 1/bl_m
 //               folded in), inverse FFT; |X_k| = |conv_k| for k < N, so the closing chirp multiply is not needed for
 //               the spectral max (float32, bl_m float2 in dynamic smem; tables built once per N by the host side)
+//           The float32 transforms (modes 1, 2) run on the frame scaled by an exact power of two taken from its mean
+//           power, so that neither the samples nor |X_k|^2 leave the float32 range whatever the input's scale is; the
+//           maximum is scaled back in float64.
 // cache_off >= 0: byte offset in dynamic smem of 2 N doubles that keep every sample's phase and amplitude between the
 //           passes (one libdevice atan2 + one hypot per sample instead of four + two; same values, same summation
 //           order, so the results do not depend on it); it may alias the FFT buffer, which is only used afterwards.
 //           -1 when it does not fit (N > 12800): the values are recomputed.
+// One frame, all 256 threads of the CTA.  This is the CAREFUL path of the library: float64 statistics with the
+// reference's own formulas (np.abs = hypot, np.angle = atan2, np.unwrap's rules, two-pass std / kurtosis, three passes for
+// feature 4: std(|abs/mean(abs) - 1|), features.py:82-85).
+template <typename CT>
+__device__ __forceinline__ void general_frame(const CT* __restrict__ iq, int64_t f, int n, int64_t frame_stride,
+                                              int64_t sample_stride, double* __restrict__ out, int64_t out_stride,
+                                              int fft_mode, const float2* __restrict__ bl_chirp,
+                                              const float2* __restrict__ bl_bfft, int bl_m, int cache_off,
+                                              unsigned char* dyn, double* red, int tid) {
+  const bool cached = cache_off >= 0;
+  double* ph_c = reinterpret_cast<double*>(dyn + (cached ? cache_off : 0));
+  double* r_c = ph_c + n;
+  const CT* base = iq + f * frame_stride;
+
+  // ---- pass 1: raw sums -----------------------------------------------------------
+  Monomials mono;
+  mono.clear();
+  double sr = 0.0, sph = 0.0, saph = 0.0, sfq = 0.0;
+  for (int i = tid; i < n; i += kGenThreads) {
+    double a, b;
+    load_strided(base, i, sample_stride, a, b);
+    mono.add(a, b);
+    const double r0 = hypot(a, b);                  // np.abs == hypot (features.py:27)
+    sr += r0;
+    const double p0 = atan2_exact(b, a);            // np.angle  (features.py:28)
+    sph += p0;
+    saph += fabs(p0);
+    if (cached) {
+      ph_c[i] = p0;
+      r_c[i] = r0;
+    } else if (i + 1 < n) {
+      double a1, b1;
+      load_strided(base, i + 1, sample_stride, a1, b1);
+      sfq += unwrap_step(atan2_exact(b1, a1) - p0) / kTwoPi;   // features.py:29-30
+    }
+  }
+  if (cached) {
+    __syncthreads();
+    for (int i = tid; i + 1 < n; i += kGenThreads) sfq += unwrap_step(ph_c[i + 1] - ph_c[i]) / kTwoPi;
+  }
+  double v1[19];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) v1[i] = mono.s[i];
+  v1[15] = sr;
+  v1[16] = sph;
+  v1[17] = saph;
+  v1[18] = sfq;
+  block_sum<19>(v1, red, tid);
+  const double dn = static_cast<double>(n);
+  const double mu_r = v1[15] / dn, mu_ph = v1[16] / dn, mu_aph = v1[17] / dn;
+  const double mu_f = v1[18] / (dn - 1.0);
+
+  // ---- pass 2: centred sums ---------------------------------------------------------
+  double v2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = tid; i < n; i += kGenThreads) {
+    double r0, p0, p1 = 0.0;
+    if (cached) {
+      r0 = r_c[i];
+      p0 = ph_c[i];
+      if (i + 1 < n) p1 = ph_c[i + 1];
+    } else {
+      double a, b;
+      load_strided(base, i, sample_stride, a, b);
+      r0 = hypot(a, b);
+      p0 = atan2_exact(b, a);
+      if (i + 1 < n) {
+        double a1, b1;
+        load_strided(base, i + 1, sample_stride, a1, b1);
+        p1 = atan2_exact(b1, a1);
+      }
+    }
+    const double d = r0 - mu_r;
+    const double d2 = d * d;
+    v2[0] += fabs(d);
+    v2[1] += d2;
+    v2[2] += d2 * d2;
+    v2[7] += fabs(r0 / mu_r - 1.0);                 // |cn_amplitude| exactly as features.py:31,84 forms it
+    const double e = p0 - mu_ph, ea = fabs(p0) - mu_aph;
+    v2[3] += e * e;
+    v2[4] += ea * ea;
+    if (i + 1 < n) {
+      const double ef = unwrap_step(p1 - p0) / kTwoPi - mu_f;
+      const double ef2 = ef * ef;
+      v2[5] += ef2;
+      v2[6] += ef2 * ef2;
+    }
+  }
+  block_sum<8>(v2, red, tid);
+
+  // ---- pass 3: spread of |cn_amplitude| about its own mean (feature 4, np.std's two passes) ----------
+  double v3[1] = {0.0};
+  {
+    const double mu_acn = v2[7] / dn;
+    for (int i = tid; i < n; i += kGenThreads) {
+      double r0;
+      if (cached) {
+        r0 = r_c[i];
+      } else {
+        double a, b;
+        load_strided(base, i, sample_stride, a, b);
+        r0 = hypot(a, b);
+      }
+      const double e = fabs(r0 / mu_r - 1.0) - mu_acn;
+      v3[0] += e * e;
+    }
+  }
+  block_sum<1>(v3, red, tid);
+
+  // ---- spectrum max -----------------------------------------------------------------
+  // exact power-of-two scale for the float32 transforms: 2^-e with 4^e ~ mean |x|^2
+  double scale = 1.0, unscale2 = 1.0;
+  {
+    const double pw = (v1[0] + v1[1]) / dn;
+    if (pw > 0.0 && pw < 1.7976931348623157e308) {
+      int e2 = 0;
+      frexp(pw, &e2);
+      const int e = e2 / 2;
+      if (e > 40 || e < -40) {                      // ordinary data is left untouched (bitwise the unscaled result)
+        scale = ldexp(1.0, -e);
+        unscale2 = ldexp(1.0, 2 * e);
+      }
+    }
+  }
+  double smax = 0.0;
+  if (fft_mode == 1) {
+    float2* buf = reinterpret_cast<float2*>(dyn);
+    __syncthreads();                                // the phase / amplitude cache (which may alias buf) is dead now
+    for (int i = tid; i < n; i += kGenThreads) {
+      double a, b;
+      load_strided(base, i, sample_stride, a, b);
+      buf[i] = make_float2(static_cast<float>(a * scale), static_cast<float>(b * scale));
+    }
+    __syncthreads();
+    smem_fft_dif(buf, n, tid);
+    for (int i = tid; i < n; i += kGenThreads) {
+      const float2 u = buf[i];
+      smax = fmax(smax, static_cast<double>(u.x) * u.x + static_cast<double>(u.y) * u.y);
+    }
+    __syncthreads();
+  } else if (fft_mode == 2) {
+    float2* buf = reinterpret_cast<float2*>(dyn);
+    __syncthreads();
+    for (int i = tid; i < bl_m; i += kGenThreads) {
+      float2 v = make_float2(0.0f, 0.0f);
+      if (i < n) {
+        double a, b;
+        load_strided(base, i, sample_stride, a, b);
+        const float2 c = bl_chirp[i];
+        const float af = static_cast<float>(a * scale), bf = static_cast<float>(b * scale);
+        v = make_float2(af * c.x - bf * c.y, af * c.y + bf * c.x);
+      }
+      buf[i] = v;
+    }
+    __syncthreads();
+    smem_fft_dif(buf, bl_m, tid);
+    for (int i = tid; i < bl_m; i += kGenThreads) {
+      const float2 u = buf[i], w = bl_bfft[i];
+      buf[i] = make_float2(u.x * w.x - u.y * w.y, u.x * w.y + u.y * w.x);
+    }
+    __syncthreads();
+    smem_ifft_dit(buf, bl_m, tid);
+    for (int i = tid; i < n; i += kGenThreads) {
+      const float2 u = buf[i];
+      smax = fmax(smax, static_cast<double>(u.x) * u.x + static_cast<double>(u.y) * u.y);
+    }
+    __syncthreads();
+  } else {
+    const double2* tw = reinterpret_cast<const double2*>(dyn);
+    for (int k = tid; k < n; k += kGenThreads) {
+      double xr = 0.0, xi = 0.0;
+      int idx = 0;
+      for (int i = 0; i < n; ++i) {
+        double a, b;
+        load_strided(base, i, sample_stride, a, b);
+        const double2 w = tw[idx];
+        xr += a * w.x - b * w.y;
+        xi += a * w.y + b * w.x;
+        idx += k;
+        if (idx >= n) idx -= n;
+      }
+      smax = fmax(smax, xr * xr + xi * xi);
+    }
+  }
+  smax = block_max(smax, red, tid);
+  if (fft_mode != 0) smax *= unscale2;
+
+  if (tid == 0) {
+    FrameSums fs;
+#pragma unroll
+    for (int i = 0; i < 15; ++i) fs.mono[i] = v1[i];
+    fs.sum_r = v1[15];
+    fs.c_abs1 = v2[0];
+    fs.c_abs2 = v3[0];
+    fs.c2 = v2[1];
+    fs.c4 = v2[2];
+    fs.ph_m2 = v2[3];
+    fs.aph_m2 = v2[4];
+    fs.f_m2 = v2[5];
+    fs.f_m4 = v2[6];
+    fs.mean_f = mu_f;
+    fs.spec_max = smax;
+    double res[18];
+    finalize_features(fs, n, res, 0);
+#pragma unroll
+    for (int i = 0; i < 18; ++i) out[f * out_stride + i] = res[i];
+  }
+}
+
+// redo_only != 0: careful-path pass behind a fused kernel - rows whose column 0 carries kRedoTagBits
+// (finalize_features) are recomputed, every other row is left alone.
 template <typename CT>
 __global__ void __launch_bounds__(kGenThreads)
 general_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int64_t frame_stride,
                         int64_t sample_stride, double* __restrict__ out, int64_t out_stride, int fft_mode,
                         const float2* __restrict__ bl_chirp, const float2* __restrict__ bl_bfft, int bl_m,
-                        int cache_off) {
+                        int cache_off, int redo_only, unsigned long long ticket) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ double red[kGenWarps * 20];
+  __shared__ int redo_rows[kGenThreads];
+  __shared__ int redo_count;
   const int tid = threadIdx.x;
+
+  if (redo_only) {
+    pdl_launch_dependents();   // whatever follows in the stream may be scheduled; it waits for this grid in turn
+    pdl_wait_primary();        // launched behind a fused kernel (possibly before it finished): its rows are visible from here
+    // nothing tagged by launch `ticket` (the slot is still below it): done - the case for ordinary data
+    if (ticket != 0 && *reinterpret_cast<volatile unsigned long long*>(&g_redo_ring[ticket & 255]) < ticket) return;
+    // each CTA scans a contiguous block of rows, 256 at a time (one coalesced-ish load per thread, one barrier)
+    const int64_t per = (n_frames + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = static_cast<int64_t>(blockIdx.x) * per;
+    const int64_t hi = lo + per < n_frames ? lo + per : n_frames;
+    for (int64_t r0 = lo; r0 < hi; r0 += kGenThreads) {
+      if (tid == 0) redo_count = 0;
+      __syncthreads();
+      const int64_t r = r0 + tid;
+      if (r < hi && static_cast<unsigned long long>(__double_as_longlong(out[r * out_stride])) == kRedoTagBits)
+        redo_rows[atomicAdd(&redo_count, 1)] = tid;   // (order is irrelevant: frames are independent)
+      __syncthreads();
+      const int cnt = redo_count;
+      for (int j = 0; j < cnt; ++j) {
+        general_frame<CT>(iq, r0 + redo_rows[j], n, frame_stride, sample_stride, out, out_stride, fft_mode, bl_chirp,
+                          bl_bfft, bl_m, cache_off, dyn, red, tid);
+        __syncthreads();
+      }
+    }
+    return;
+  }
 
   if (fft_mode == 0) {  // twiddle table once per CTA
     double2* tw = reinterpret_cast<double2*>(dyn);
@@ -120,168 +361,10 @@ general_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int6
     }
     __syncthreads();
   }
-
-  const bool cached = cache_off >= 0;
-  double* ph_c = reinterpret_cast<double*>(dyn + (cached ? cache_off : 0));
-  double* r_c = ph_c + n;
-
   for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
-    const CT* base = iq + f * frame_stride;
-
-    // ---- pass 1: raw sums -----------------------------------------------------------
-    Monomials mono;
-    mono.clear();
-    double sr = 0.0, sph = 0.0, saph = 0.0, sfq = 0.0;
-    for (int i = tid; i < n; i += kGenThreads) {
-      double a, b;
-      load_strided(base, i, sample_stride, a, b);
-      mono.add(a, b);
-      const double r0 = hypot(a, b);                  // np.abs == hypot (features.py:27)
-      sr += r0;
-      const double p0 = atan2_exact(b, a);            // np.angle  (features.py:28)
-      sph += p0;
-      saph += fabs(p0);
-      if (cached) {
-        ph_c[i] = p0;
-        r_c[i] = r0;
-      } else if (i + 1 < n) {
-        double a1, b1;
-        load_strided(base, i + 1, sample_stride, a1, b1);
-        sfq += unwrap_step(atan2_exact(b1, a1) - p0) / kTwoPi;   // features.py:29-30
-      }
-    }
-    if (cached) {
-      __syncthreads();
-      for (int i = tid; i + 1 < n; i += kGenThreads) sfq += unwrap_step(ph_c[i + 1] - ph_c[i]) / kTwoPi;
-    }
-    double v1[19];
-#pragma unroll
-    for (int i = 0; i < 15; ++i) v1[i] = mono.s[i];
-    v1[15] = sr;
-    v1[16] = sph;
-    v1[17] = saph;
-    v1[18] = sfq;
-    block_sum<19>(v1, red, tid);
-    const double dn = static_cast<double>(n);
-    const double mu_r = v1[15] / dn, mu_ph = v1[16] / dn, mu_aph = v1[17] / dn;
-    const double mu_f = v1[18] / (dn - 1.0);
-
-    // ---- pass 2: centred sums ---------------------------------------------------------
-    double v2[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int i = tid; i < n; i += kGenThreads) {
-      double r0, p0, p1 = 0.0;
-      if (cached) {
-        r0 = r_c[i];
-        p0 = ph_c[i];
-        if (i + 1 < n) p1 = ph_c[i + 1];
-      } else {
-        double a, b;
-        load_strided(base, i, sample_stride, a, b);
-        r0 = hypot(a, b);
-        p0 = atan2_exact(b, a);
-        if (i + 1 < n) {
-          double a1, b1;
-          load_strided(base, i + 1, sample_stride, a1, b1);
-          p1 = atan2_exact(b1, a1);
-        }
-      }
-      const double d = r0 - mu_r;
-      const double d2 = d * d;
-      v2[0] += fabs(d);
-      v2[1] += d2;
-      v2[2] += d2 * d2;
-      const double e = p0 - mu_ph, ea = fabs(p0) - mu_aph;
-      v2[3] += e * e;
-      v2[4] += ea * ea;
-      if (i + 1 < n) {
-        const double ef = unwrap_step(p1 - p0) / kTwoPi - mu_f;
-        const double ef2 = ef * ef;
-        v2[5] += ef2;
-        v2[6] += ef2 * ef2;
-      }
-    }
-    block_sum<7>(v2, red, tid);
-
-    // ---- spectrum max -----------------------------------------------------------------
-    double smax = 0.0;
-    if (fft_mode == 1) {
-      float2* buf = reinterpret_cast<float2*>(dyn);
-      for (int i = tid; i < n; i += kGenThreads) {
-        double a, b;
-        load_strided(base, i, sample_stride, a, b);
-        buf[i] = make_float2(static_cast<float>(a), static_cast<float>(b));
-      }
-      __syncthreads();
-      smem_fft_dif(buf, n, tid);
-      for (int i = tid; i < n; i += kGenThreads) {
-        const float2 u = buf[i];
-        smax = fmax(smax, static_cast<double>(u.x) * u.x + static_cast<double>(u.y) * u.y);
-      }
-      __syncthreads();
-    } else if (fft_mode == 2) {
-      float2* buf = reinterpret_cast<float2*>(dyn);
-      for (int i = tid; i < bl_m; i += kGenThreads) {
-        float2 v = make_float2(0.0f, 0.0f);
-        if (i < n) {
-          double a, b;
-          load_strided(base, i, sample_stride, a, b);
-          const float2 c = bl_chirp[i];
-          const float af = static_cast<float>(a), bf = static_cast<float>(b);
-          v = make_float2(af * c.x - bf * c.y, af * c.y + bf * c.x);
-        }
-        buf[i] = v;
-      }
-      __syncthreads();
-      smem_fft_dif(buf, bl_m, tid);
-      for (int i = tid; i < bl_m; i += kGenThreads) {
-        const float2 u = buf[i], w = bl_bfft[i];
-        buf[i] = make_float2(u.x * w.x - u.y * w.y, u.x * w.y + u.y * w.x);
-      }
-      __syncthreads();
-      smem_ifft_dit(buf, bl_m, tid);
-      for (int i = tid; i < n; i += kGenThreads) {
-        const float2 u = buf[i];
-        smax = fmax(smax, static_cast<double>(u.x) * u.x + static_cast<double>(u.y) * u.y);
-      }
-      __syncthreads();
-    } else {
-      const double2* tw = reinterpret_cast<const double2*>(dyn);
-      for (int k = tid; k < n; k += kGenThreads) {
-        double xr = 0.0, xi = 0.0;
-        int idx = 0;
-        for (int i = 0; i < n; ++i) {
-          double a, b;
-          load_strided(base, i, sample_stride, a, b);
-          const double2 w = tw[idx];
-          xr += a * w.x - b * w.y;
-          xi += a * w.y + b * w.x;
-          idx += k;
-          if (idx >= n) idx -= n;
-        }
-        smax = fmax(smax, xr * xr + xi * xi);
-      }
-    }
-    smax = block_max(smax, red, tid);
-
-    if (tid == 0) {
-      FrameSums fs;
-#pragma unroll
-      for (int i = 0; i < 15; ++i) fs.mono[i] = v1[i];
-      fs.sum_r = v1[15];
-      fs.c_abs1 = v2[0];
-      fs.c2 = v2[1];
-      fs.c4 = v2[2];
-      fs.ph_m2 = v2[3];
-      fs.aph_m2 = v2[4];
-      fs.f_m2 = v2[5];
-      fs.f_m4 = v2[6];
-      fs.mean_f = mu_f;
-      fs.spec_max = smax;
-      double res[18];
-      finalize_features(fs, n, res);
-#pragma unroll
-      for (int i = 0; i < 18; ++i) out[f * out_stride + i] = res[i];
-    }
+    general_frame<CT>(iq, f, n, frame_stride, sample_stride, out, out_stride, fft_mode, bl_chirp, bl_bfft, bl_m,
+                      cache_off, dyn, red, tid);
+    __syncthreads();
   }
 }
 

@@ -122,7 +122,8 @@ __device__ __forceinline__ void large_stage16(float2* __restrict__ buf, const fl
 template <int N, typename CT>
 __global__ void __launch_bounds__(LargeCfg<N>::THREADS, LargeCfg<N>::MIN_BLOCKS)
 large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame_stride,
-                      double* __restrict__ out, int64_t out_stride) {
+                      double* __restrict__ out, int64_t out_stride, unsigned long long ticket) {
+  pdl_launch_dependents();   // the careful-path kernel may be launched now; it waits for this grid to complete
   using Cfg = LargeCfg<N>;
   constexpr int THREADS = Cfg::THREADS, WARPS = Cfg::WARPS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -132,8 +133,8 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
   double* pend = reinterpret_cast<double*>(smem_raw + Cfg::FFT_BYTES + Cfg::PHI_BYTES + Cfg::PART_BYTES);
   const int my_frames = blockIdx.x < n_frames ? static_cast<int>((n_frames - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr unsigned FULL = 0xffffffffu;
 
+  pdl_wait_primary();          // the predecessor in the stream has completed: global memory may be touched
   int it = 0;
   for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x, ++it) {
     const CT* x = iq + f * frame_stride;
@@ -346,7 +347,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
           fs.mean_f = pl[23] / (N - 1);
           fs.spec_max = pl[24];
           const int64_t fo = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it - bi + lane) * gridDim.x;
-          finalize_features(fs, N, out + fo * out_stride);
+          finalize_features(fs, N, out + fo * out_stride, kCheckAll, ticket);
         }
         __syncwarp();
       }

@@ -14,7 +14,7 @@
 // registers (the unified kernel needs 168: 12 warps), and every scheduler always holds FP64-heavy and
 // FP32-heavy warps side by side.
 #pragma once
-#include "amc_fused16.cuh"
+#include "../amc_fused16.cuh"
 
 namespace amc {
 
@@ -142,7 +142,7 @@ fusedws_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
           fs.mean_f = pl[23] / (N - 1);
           fs.spec_max = pl[24];
           const int64_t fo = gg + static_cast<int64_t>(k - bi + lane) * tg;
-          finalize_features(fs, N, out + fo * out_stride);
+          finalize_features(fs, N, out + fo * out_stride, kCheckAll);
         }
         __syncwarp();
       }

@@ -61,7 +61,7 @@ def feature_mask_of(feature_ids) -> int:
 
 
 def extract_features(iq, out=None, stream=None, force_general: bool = False, feature_mask: int = nat.AMC_ALL_FEATURES,
-                     spt8: bool = False, ws: bool = False, direct_dft: bool = False, relayout: bool = True):
+                     direct_dft: bool = False, relayout: bool = True, extra_flags: int = 0):
     """All 18 features of every frame of a device-resident complex tensor.
 
     feature_mask (default: all 18): the features the caller will read.  The library may skip the work of
@@ -71,8 +71,7 @@ def extract_features(iq, out=None, stream=None, force_general: bool = False, fea
     iq  : CUDA tensor (..., frame_size), complex128 or complex64 (north_star's batched entry takes
           (n_snr, n_frames, frame_size)).
     out : optional CUDA float64 tensor (..., 18), C-contiguous.
-    spt8: A/B switch - run the first-generation 8-samples-per-thread fused kernel.
-    ws  : A/B switch - run the warp-specialised (FP64 warps / FP32 warps) variant, N = 2048 only.
+    extra_flags: raw C-ABI flag bits OR-ed in (A/B experiment kernels of a -DAMC_EXPERIMENTS build only).
     relayout: sample-major device tensors of a fused frame size are re-laid-out into a scratch tensor first
           (False: the general kernel reads them in place).
     direct_dft: cross-check switch - frame sizes that are not powers of two use the float64 direct DFT (O(N^2))
@@ -98,8 +97,8 @@ def extract_features(iq, out=None, stream=None, force_general: bool = False, fea
         rc = nat.lib().amc_extract_batch(
             x.data_ptr(), _dtype_code(x), n_frames, n, x.stride(0) if n_frames > 1 else n, x.stride(1) if n > 1 else 1,
             out.data_ptr(), N_FEATURES, feature_mask,
-            (nat.AMC_FLAG_FORCE_GENERAL if force_general else 0) | (nat.AMC_FLAG_FUSED_SPT8 if spt8 else 0)
-            | (nat.AMC_FLAG_FUSED_WS if ws else 0) | (nat.AMC_FLAG_DIRECT_DFT if direct_dft else 0),
+            (nat.AMC_FLAG_FORCE_GENERAL if force_general else 0) | (nat.AMC_FLAG_DIRECT_DFT if direct_dft else 0)
+            | int(extra_flags),
             _stream_ptr(stream),
         )
     nat.check(rc)

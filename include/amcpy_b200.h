@@ -34,9 +34,20 @@
  *   relative 1e-6 : features 1, 2, 3, 5, 9 (float32 FFT / atan2 in the fused kernel; unwrap branch
  *                   decisions within 4e-6 rad of +-pi are re-decided in float64 exactly as np.unwrap)
  *   AMC_FLAG_FORCE_GENERAL computes everything except the FFT in float64.
+ * The fused kernels hold these classes for every frame because the few kinds of frame their float32 parts cannot
+ * handle are detected from the frame's own sums and recomputed by the general (float64) kernel in a second, tiny
+ * launch that follows every fused launch ("careful path": mean power outside [2^-100, 2^80*2048/N] - float32 would
+ * under/overflow -, phase / |phase| / frequency spread below 0.1 rad - an unmodulated carrier or a dominant DC line,
+ * where float32 phase noise would show -, and a degenerate |r - mean r| distribution for feature 4).  Supported
+ * input range: any finite complex128 / complex64 values whose |x|^6 sums stay finite in float64 (the reference itself
+ * overflows beyond that); a single sample below 1e-37 inside a frame of ordinary scale is treated as 0 by the
+ * float32 phase path.
+ * complex64 input is widened exactly and computed like complex128 (the reference's numpy computes complex64 frames in
+ * float32 and differs from its own complex128 result by ~4e-7; this library matches the widened result at the
+ * tolerances above and the float32-numpy result at 2e-4).
  * General-kernel spectrum: power-of-two sizes <= 16384 by a float32 radix-2 FFT; other sizes from 128 to 8192 by a
  * float32 Bluestein (chirp-z) FFT; smaller sizes and 8193..12288 by a float64 direct DFT; anything larger returns
- * AMC_ERR_UNSUPPORTED.
+ * AMC_ERR_UNSUPPORTED.  The float32 transforms run on the frame scaled by an exact power of two.
  */
 #ifndef AMCPY_B200_H
 #define AMCPY_B200_H
@@ -57,9 +68,13 @@ extern "C" {
 
 /* flags */
 #define AMC_FLAG_FORCE_GENERAL 1 /* never take the fused fixed-size kernel */
-#define AMC_FLAG_FUSED_SPT8 2     /* fused kernel variant with 8 samples per thread (kept for N=256 and for A/B runs) */
-#define AMC_FLAG_FUSED_WS 4       /* N = 2048 only: warp-specialised variant (FP64 warps / FP32 warps), A/B runs */
 #define AMC_FLAG_DIRECT_DFT 8     /* non-power-of-two sizes: float64 direct DFT instead of the float32 Bluestein FFT (cross-check) */
+/* Unknown flag bits are rejected with AMC_ERR_INVALID_ARG.  Bits 2 and 4 select A/B experiment kernels that exist
+ * only in a library built with -DAMC_EXPERIMENTS (tools/exp/); they are not part of this ABI. */
+#ifdef AMC_EXPERIMENTS
+#define AMC_FLAG_FUSED_SPT8 2 /* round-1 kernel with 8 samples per thread */
+#define AMC_FLAG_FUSED_WS 4   /* N = 2048: warp-specialised variant (FP64 warps / FP32 warps) */
+#endif
 
 /* return codes */
 #define AMC_OK 0
@@ -71,6 +86,22 @@ extern "C" {
 /* Library / ABI version (major*1000 + minor). */
 int amc_version(void);
 
+/*
+ * Optional eager initialisation of `device`: builds the twiddle tables of the fused kernels and waits for them.
+ * Without it the first amc_extract_batch call on a device builds them on an internal stream and makes the caller's
+ * stream wait for them on the device (cudaStreamWaitEvent; no host synchronisation) - which is not allowed while
+ * that stream is being captured into a CUDA graph: call amc_init first in that case.
+ */
+int amc_init(int device);
+
+/*
+ * Device memory (bytes) the library itself allocates - once, cached - for calls of this shape: Bluestein tables of a
+ * non-power-of-two frame_size (amc_extract_batch) and, when host_path != 0, the double-buffered chunk buffers of
+ * amc_extract_host / amc_extract_host_planar.  0 for the device-pointer path at power-of-two sizes: the caller owns
+ * every buffer there.  Negative = AMC_ERR_*.
+ */
+int64_t amc_workspace_bytes(int iq_dtype, int64_t n_frames, int64_t frame_size, int host_path);
+
 /* Message of the last failing call made by THIS thread ("" if none). Never NULL. */
 const char* amc_last_error_string(void);
 
@@ -79,10 +110,11 @@ int amc_device_count(void);
 
 /*
  * All 18 features of n_frames frames that already live in device memory (current device),
- * enqueued on `cuda_stream` (a cudaStream_t, may be NULL for the default stream); does not
- * synchronise, does not allocate - except that the FIRST call on a device (twiddle tables) and the first
- * call for a new non-power-of-two frame size (Bluestein tables, <= 192 KB, cached per device and size)
- * build their tables and wait for that once.
+ * enqueued on `cuda_stream` (a cudaStream_t, may be NULL for the default stream); never synchronises the
+ * host with the device.  The FIRST call on a device (twiddle tables, see amc_init) and the first call for a new
+ * non-power-of-two frame size (Bluestein tables, <= 192 KB of device memory, cached per device and size: see
+ * amc_workspace_bytes) build their tables on an internal stream; `cuda_stream` waits for them on the device.
+ * A fused launch is followed by the careful-path launch described above (two kernels per call).
  *   iq           device pointer, complex64/complex128 interleaved
  *   out          device pointer, float64, row f at out + f*out_stride, out_stride >= 18
  *   feature_mask bit k = feature k+1 wanted; must be non-zero.  All 18 columns are always written: a wanted

@@ -24,3 +24,36 @@ def hard_case_inputs(n: int) -> np.ndarray:
     x[8, 0] = complex(np.nan, x[8, 0].imag)
     x[9, n - 1] = complex(x[9, n - 1].real, np.nan)
     return x
+
+
+NARROW_SIZES = (256, 2048, 8192)
+
+def narrow_case_inputs(n: int) -> np.ndarray:
+    """10 frames of `n` samples that the float32 parts of the fused kernels cannot handle on their own (round-2 soak
+    findings + ADVICE.md): 0 unmodulated carrier at 40 dB, 1 carrier at phase 2.0 rad / 50 dB, 2 WGN 26 dB below a DC
+    line (phase spread 0.025 rad: the round-1 soak case), 3 carrier at 60 dB with a slow 1e-4 cycles/sample rotation,
+    4 QPSK scaled by 1e-30, 5 16QAM scaled by 1e+20, 6 noise-free two-level amplitude (|x| in {1, 3}, every
+    |cn_amplitude| equal: the reference's feature 4 is an exact 0), 7 two-level amplitude at 70 dB SNR, 8 WGN scaled by
+    1e-25, 9 BPSK at 18 dB scaled by 3e+17."""
+    rng = np.random.default_rng(4242 + n)
+    k = np.arange(n)
+
+    def noise(db):
+        s = 10.0 ** (-db / 20.0) / np.sqrt(2.0)
+        return s * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+
+    lvl = np.where(np.arange(n) % 2 == 0, 1.0, 3.0)
+    ph = np.exp(1j * rng.uniform(-np.pi, np.pi, n))
+    x = np.stack([
+        1.0 + noise(40.0),
+        np.exp(2.0j) * (1.0 + noise(50.0)),
+        (1.0 + 0.0j) + noise(26.0),
+        np.exp(2j * np.pi * 1e-4 * k) * (1.0 + noise(60.0)),
+        synth.frame(1, 12.0, 11, 4, n, 78) * 1e-30,
+        synth.frame(3, 16.0, 13, 5, n, 78) * 1e20,
+        lvl * ph,
+        lvl * ph + noise(70.0),
+        synth.frame(5, 0.0, 5, 8, n, 78) * 1e-25,
+        synth.frame(0, 18.0, 14, 9, n, 78) * 3e17,
+    ])
+    return x

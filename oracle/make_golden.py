@@ -32,7 +32,7 @@ from amcpy.features import (  # noqa: E402
 )
 
 from amcpy_b200 import synth  # noqa: E402
-from oracle.hard_cases import HARD_SIZES, hard_case_inputs  # noqa: E402
+from oracle.hard_cases import HARD_SIZES, NARROW_SIZES, hard_case_inputs, narrow_case_inputs  # noqa: E402
 
 GOLD = ROOT / "tests" / "golden"
 SEED = 2024
@@ -59,8 +59,19 @@ def hard_cases() -> None:
                  features_c64=ref_features(x64))
 
 
+def narrow_cases() -> None:
+    """Outputs of the unmodified reference on oracle/hard_cases.py:narrow_case_inputs - the frames the fused kernels
+    hand to the careful (float64) path: narrow phase clusters, extreme scales, degenerate amplitude distributions."""
+    for n in NARROW_SIZES:
+        x = narrow_case_inputs(n)
+        np.savez(GOLD / f"narrow_n{n}.npz", n=n, input_sha256=sha(x), features=ref_features(x))
+
+
 def main() -> None:
     GOLD.mkdir(parents=True, exist_ok=True)
+    if "--narrow-only" in sys.argv:
+        narrow_cases()
+        return
     if "--hard-only" in sys.argv:      # leaves the other fixtures (and their zip timestamps) untouched
         hard_cases()
         return
@@ -128,6 +139,7 @@ def main() -> None:
 
     # 6. hard cases
     hard_cases()
+    narrow_cases()
 
     for p in sorted(GOLD.glob("*.npz")):
         print(p.name, os.path.getsize(p))

@@ -105,6 +105,16 @@ def golden_hard(n):
     return x, g["features"], g["features_c64"]
 
 
+def golden_narrow(n):
+    """Inputs (regenerated, checked by hash) and reference outputs of tests/golden/narrow_n{n}.npz: (x[10, n], features[10, 18])."""
+    from oracle.hard_cases import narrow_case_inputs
+
+    g = load_golden(f"narrow_n{n}.npz")
+    x = narrow_case_inputs(n)
+    assert sha(x) == str(g["input_sha256"]), "narrow-case inputs drifted from the golden fixture"
+    return x, g["features"]
+
+
 def assert_features_close(got, want, *, scale=1.0, ids=range(1, 19)):
     """Per-feature relative tolerance classes of BASELINE.json north_star (written here):
     1e-6 on FFT/atan2-derived features (1,2,3,5,9), 1e-9 on all others."""

@@ -28,12 +28,10 @@ LOOSE = (1, 2, 3, 5, 9)
 
 
 def loose_rtol(want):
-    """Per-frame tolerance of the float32 class (features 1, 2, 3, 5, 9): 1e-6, relaxed for frames whose phase barely
-    moves (an unmodulated carrier / DC line above ~30 dB SNR): float32 phases carry ~1e-7 rad of rounding noise, which
-    is 4e-7 / sigma relative to phase statistics of spread sigma (known limits)."""
-    sigma = np.minimum(np.minimum(want[:, 1], want[:, 2]), 2.0 * np.pi * want[:, 4])
-    with np.errstate(all="ignore"):
-        return np.where(sigma > 0, np.maximum(1e-6, 4e-7 / sigma), 1e-6)
+    """Per-frame tolerance of the float32 class (features 1, 2, 3, 5, 9): 1e-6 for EVERY frame - narrow phase clusters
+    (unmodulated carriers, DC lines up to 60 dB SNR) and extreme scales are handed to the float64 path by the
+    library itself (round 1 relaxed this to 4e-7 / sigma)."""
+    return np.full(want.shape[0], 1e-6)
 
 
 def check(got, want, what, loose):
@@ -41,9 +39,14 @@ def check(got, want, what, loose):
         rtol = loose if fid in LOOSE else 1e-9
         g, w = got[:, fid - 1], want[:, fid - 1]
         both_nan = np.isnan(g) & np.isnan(w)
-        # feature 4 is the square root of a difference (sum d^2 - (sum|d|)^2/N): an exact 0 (all |cn| equal) comes
-        # out as ~1e-8 |cn| instead of the reference's ~1e-17, so it gets an absolute floor
-        floor = 1e-7 if fid == 4 else 1e-300
+        # feature 4 of a frame whose |cn| are all equal is rounding noise around an exact 0 in the reference (1e-16)
+        floor = 1e-12 if fid == 4 else 1e-300
+        if fid >= 10:
+            # cumulants are differences of moments of size C21^(order/2): when such a difference happens to cancel to
+            # less than 1e-4 of its terms (a chance event on noise-like frames) 1e-9 RELATIVE to the remainder is below the
+            # float64 rounding of the terms themselves - for the reference's own pairwise sums as much as for ours
+            order = {10: 1, 11: 1, 12: 2, 13: 2, 14: 2}.get(fid, 3)
+            floor = 1e-4 * np.abs(want[:, 10]) ** order
         err = np.abs(g - w) / np.maximum(np.abs(w), floor)
         err[both_nan] = 0.0
         if not (err <= rtol).all():
@@ -67,7 +70,13 @@ while (cases < args.cases) if args.cases > 0 else (time.time() < t_end):
             fr = fr * np.exp(2j * np.pi * rng.uniform(-0.5, 0.5) * np.arange(n) + 1j * rng.uniform(0, 6.28))
         if rng.random() < 0.3:
             fr = fr + complex(rng.normal(), rng.normal()) * rng.uniform(0, 2)
-        x[f] = fr * 10.0 ** rng.uniform(-4, 4)
+        kind = rng.random()
+        if kind < 0.12:      # unmodulated carrier / DC-dominated frame, 20 .. 60 dB: phase spread down to 1e-3 rad
+            amp = 10.0 ** (-rng.uniform(20, 60) / 20.0) / np.sqrt(2.0)
+            fr = np.exp(1j * rng.uniform(-3.14, 3.14)) * (1.0 + amp * (rng.standard_normal(n) + 1j * rng.standard_normal(n)))
+            if rng.random() < 0.5:
+                fr = fr * np.exp(2j * np.pi * rng.uniform(-2e-4, 2e-4) * np.arange(n))
+        x[f] = fr * 10.0 ** (rng.uniform(-30, 20) if rng.random() < 0.1 else rng.uniform(-4, 4))
     if c64:
         x = x.astype(np.complex64)
     with np.errstate(all="ignore"):

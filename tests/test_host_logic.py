@@ -116,7 +116,7 @@ def test_product_never_imports_the_oracle():
             elif isinstance(node, ast.ImportFrom):
                 names = [node.module or ""]
             assert not any(n.split(".")[0] == "oracle" for n in names), f"{py} imports the oracle"
-    for cu in (ROOT / "amcpy_b200" / "csrc").iterdir():
+    for cu in (ROOT / "amcpy_b200" / "csrc").rglob("*.cu*"):
         assert "oracle" not in cu.read_text()
 
 
