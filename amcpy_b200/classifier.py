@@ -3,25 +3,69 @@ the hot path.  Same recipe as the reference so that `amcpy full` completes on th
 MLP n_used -> 26 -> 29 -> 30 -> n_classes, BatchNorm + activation + Dropout after every hidden
 Linear, Softmax output fed to CrossEntropyLoss (sic), RMSprop lr 1.418e-3, batch 128, 21 epochs
 (/root/reference/src/amcpy/nn_model.py:28-75, :88-198; config.py:151-171), per-SNR accuracy
-(nn_model.py:227-267), checkpoint `ann/model-<id>.pt` (nn_model.py:175-185)."""
+(nn_model.py:227-267), checkpoint `ann/model-<id>.pt` in the reference's format (nn_model.py:175-185, :201-219:
+state-dict keys `layers.N.*`, loadable by the reference's `load_model` and vice versa)."""
 
 from __future__ import annotations
 
 import uuid
 
 import numpy as np
+import torch.nn as nn
+
+
+class AMCClassifier(nn.Module):
+    """The reference's classifier (nn_model.py:28-75).  The Sequential lives under the attribute `layers`, so the
+    state-dict keys are `layers.0.weight` ... `layers.12.bias` - the layout `load_model` (nn_model.py:201-219) expects."""
+
+    def __init__(self, n_features: int, n_classes: int, hl1: int = 26, hl2: int = 29, hl3: int = 30,
+                 dropout: float = 0.4, activation: str = "relu") -> None:
+        super().__init__()
+        act = {"relu": nn.ReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid}.get(activation, nn.ReLU)
+        mods, width = [], n_features
+        for h in (hl1, hl2, hl3):
+            mods += [nn.Linear(width, h), nn.BatchNorm1d(h), act(), nn.Dropout(dropout)]
+            width = h
+        mods += [nn.Linear(width, n_classes), nn.Softmax(dim=1)]
+        self.layers = nn.Sequential(*mods)
+
+    def forward(self, x):
+        return self.layers(x)
 
 
 def build_model(n_features: int, n_classes: int, hidden=(26, 29, 30), dropout: float = 0.4, activation: str = "relu"):
-    import torch.nn as nn
+    return AMCClassifier(n_features, n_classes, *hidden, dropout=dropout, activation=activation)
 
-    act = {"relu": nn.ReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid}.get(activation, nn.ReLU)
-    layers, width = [], n_features
-    for h in hidden:
-        layers += [nn.Linear(width, h), nn.BatchNorm1d(h), act(), nn.Dropout(dropout)]
-        width = h
-    layers += [nn.Linear(width, n_classes), nn.Softmax(dim=1)]
-    return nn.Sequential(*layers)
+
+def model_for(cfg):
+    t = cfg.training
+    return build_model(cfg.features.num_used, len(cfg.signals.modulations_with_noise),
+                       (t.layer_size_hl1, t.layer_size_hl2, t.layer_size_hl3), t.dropout, t.activation)
+
+
+def save_model(model, model_id: str, cfg):
+    """`ann/model-<id>.pt` with the reference's keys (nn_model.py:175-185): model_state_dict / model_id / config (the
+    Config object itself, as the reference stores its own)."""
+    import torch
+
+    cfg.paths.trained_ann.mkdir(parents=True, exist_ok=True)
+    path = cfg.paths.trained_ann / f"model-{model_id}.pt"
+    state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    torch.save({"model_state_dict": state, "model_id": model_id, "config": cfg}, path)
+    return path
+
+
+def load_model(model_id: str, cfg):
+    """nn_model.py:201-219: rebuild the architecture from cfg, load `model_state_dict`, eval mode.  Reads checkpoints
+    written here and by the reference alike (same keys)."""
+    import torch
+
+    path = cfg.paths.trained_ann / f"model-{model_id}.pt"
+    checkpoint = torch.load(path, map_location="cpu", weights_only=False)
+    model = model_for(cfg)
+    model.load_state_dict(checkpoint["model_state_dict"])
+    model.eval()
+    return model
 
 
 def train_classifier(cfg, x_train, y_train, x_test, y_test, device=None, epochs: int | None = None, seed: int = 0,
@@ -39,10 +83,13 @@ def train_classifier(cfg, x_train, y_train, x_test, y_test, device=None, epochs:
     opt_cls = {"rmsprop": torch.optim.RMSprop, "adam": torch.optim.Adam}.get(t.optimizer, torch.optim.NAdam)
     opt = opt_cls(model.parameters(), lr=t.learning_rate)
     loss_fn = nn.CrossEntropyLoss()
-    xt = torch.as_tensor(np.asarray(x_train, dtype=np.float32), device=device)
-    yt = torch.as_tensor(np.asarray(y_train), dtype=torch.long, device=device)
-    xv = torch.as_tensor(np.asarray(x_test, dtype=np.float32), device=device)
-    yv = torch.as_tensor(np.asarray(y_test), dtype=torch.long, device=device)
+    def dev(a, dt):   # device tensors from the device consumer pass through; host arrays are uploaded once
+        if isinstance(a, torch.Tensor):
+            return a.to(device=device, dtype=dt)
+        return torch.as_tensor(np.asarray(a), dtype=dt, device=device)
+
+    xt, yt = dev(x_train, torch.float32), dev(y_train, torch.long)
+    xv, yv = dev(x_test, torch.float32), dev(y_test, torch.long)
     hist = {"loss": [], "accuracy": [], "val_loss": [], "val_accuracy": []}
     n = xt.shape[0]
     for ep in range(epochs if epochs is not None else t.epochs):
@@ -72,11 +119,7 @@ def train_classifier(cfg, x_train, y_train, x_test, y_test, device=None, epochs:
             print(f"Epoch {ep + 1:3d} | loss {hist['loss'][-1]:.4f} | acc {hist['accuracy'][-1]:.4f} | "
                   f"val_loss {hist['val_loss'][-1]:.4f} | val_acc {hist['val_accuracy'][-1]:.4f}")
     model_id = uuid.uuid4().hex[:8]
-    cfg.paths.trained_ann.mkdir(parents=True, exist_ok=True)
-    torch.save({"model_state_dict": model.state_dict(), "model_id": model_id,
-                "config": {"used": list(cfg.features.used), "hidden": [t.layer_size_hl1, t.layer_size_hl2, t.layer_size_hl3],
-                           "dropout": t.dropout, "activation": t.activation}},
-               cfg.paths.trained_ann / f"model-{model_id}.pt")
+    save_model(model, model_id, cfg)
     return model, model_id, hist
 
 

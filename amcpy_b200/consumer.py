@@ -91,8 +91,37 @@ def standardize_device(x):
     return ((x64 - mean) / scale).to(torch.float32), mean, scale
 
 
+def split_indices(y, test_size: float, random_state: int):
+    """(train_idx, test_idx): EXACTLY the partition `train_test_split(..., test_size, random_state, stratify=y)` applies
+    (preprocessing.py:65-71) - sklearn's own StratifiedShuffleSplit run on the integer labels on the host (its
+    Mersenne-Twister stream is part of the reference's result; the feature rows never leave the device)."""
+    from sklearn.model_selection import train_test_split
+
+    y = np.asarray(y)
+    tr, te = train_test_split(np.arange(y.shape[0]), test_size=test_size, random_state=random_state, stratify=y)
+    return tr, te
+
+
+def load_feature_set_device(cfg: Config, feats: dict, mode: str = "training"):
+    """Device-resident `preprocess_data` (preprocessing.py:13-75 with the (6, N) -> (N, 6) transpose of :55 fixed):
+    feats {MOD: CUDA tensor (n_snr, n_frames, 18)} -> x_train, x_test, y_train, y_test (CUDA tensors, float32 / int64)
+    and a `Standardizer` holding the fitted mean_ / scale_ (numpy) for later evaluation.  Same values and the same
+    partition as the host consumer `load_feature_set`."""
+    import torch
+
+    x, y = stack_features_device(cfg, feats, mode)
+    xs, mean, scale = standardize_device(x)
+    tr, te = split_indices(y.cpu().numpy(), cfg.training.test_size, cfg.training.random_state)
+    tr_d, te_d = torch.as_tensor(tr, device=x.device), torch.as_tensor(te, device=x.device)
+    scaler = Standardizer()
+    scaler.mean_, scaler.scale_ = mean.cpu().numpy(), scale.cpu().numpy()
+    return xs[tr_d], xs[te_d], y[tr_d], y[te_d], scaler
+
+
 def stratified_split_device(x, y, test_size: float, seed: int):
-    """Per-class random split (same class proportions in both parts), all on the device."""
+    """Per-class random split (same class proportions in both parts), all on the device, with torch's generator.
+    NOT the reference's partition - `load_feature_set_device` uses `split_indices` for that; this one is for callers
+    that only need a stratified split and want no host round trip at all."""
     import torch
 
     g = torch.Generator(device=x.device).manual_seed(seed)

@@ -15,7 +15,7 @@ import argparse
 from pathlib import Path
 
 from .config import Config, Paths, SignalConfig
-from .feature_extraction import run_extraction
+from .feature_extraction import extract_all, run_extraction
 
 
 def _build_parser() -> argparse.ArgumentParser:
@@ -43,7 +43,8 @@ def _config(args) -> Config:
 
 def _init_distributed_if_launched() -> int:
     """Under torchrun (WORLD_SIZE > 1) join the process group so that run_extraction's closing barrier works
-    (ranks take every world_size-th modulation on their own GPU).  Host-side rendezvous only: gloo."""
+    (every rank extracts a contiguous shard of the flattened (modulation, frame, snr) space; rank 0 assembles and writes
+    the files).  Host-side exchange of the small feature blocks only: gloo."""
     import os
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -72,18 +73,25 @@ def cmd_synth(cfg: Config, args) -> None:
 
 
 def cmd_full(cfg: Config, args=None) -> None:
-    from .classifier import accuracy_by_snr, train_classifier
-    from .consumer import load_feature_set
+    """extract -> feature consumer -> classifier, the matrices handed over in memory (main.py:153-157 chains the
+    stages through calculated-features/*.mat; the files are still written - they are the stage's contract)."""
+    import torch
 
-    cmd_extract(cfg)
-    if _init_distributed_if_launched() != 0:
+    from .classifier import accuracy_by_snr, train_classifier
+    from .consumer import load_feature_set_device
+
+    rank = _init_distributed_if_launched()
+    mats = extract_all(cfg)
+    if rank != 0:
         return                                   # the classifier is a single-GPU job: rank 0 trains
-    x_train, x_test, y_train, y_test, scaler = load_feature_set(cfg, mode="training")
+    dev = torch.device("cuda", int(__import__("os").environ.get("LOCAL_RANK", "0")) % max(1, torch.cuda.device_count()))
+    feats = {m: torch.from_numpy(v).to(dev) for m, v in mats.items()}    # float32 (n_snr, n_frames, 18), as in the .mat
+    x_train, x_test, y_train, y_test, scaler = load_feature_set_device(cfg, feats, mode="training")
     print(f"feature set ready: train {tuple(x_train.shape)}, test {tuple(x_test.shape)}, "
-          f"{len(set(y_train.tolist()))} classes")
-    model, model_id, hist = train_classifier(cfg, x_train, y_train, x_test, y_test,
+          f"{int(torch.unique(y_train).numel())} classes")
+    model, model_id, hist = train_classifier(cfg, x_train, y_train, x_test, y_test, device=dev,
                                              epochs=getattr(args, "epochs", None))
-    acc = accuracy_by_snr(model, scaler, cfg)
+    acc = accuracy_by_snr(model, scaler, cfg, matrices=mats)
     print(f"model {model_id}: val_acc {hist['val_accuracy'][-1]:.4f}; accuracy by SNR index: "
           + ", ".join(f"{k}:{v:.2f}" for k, v in acc.items()))
 
