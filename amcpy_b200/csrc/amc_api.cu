@@ -155,7 +155,8 @@ struct BluesteinTables {
 std::map<std::pair<int, int64_t>, BluesteinTables> g_bluestein;
 constexpr size_t kBluesteinMaxEntries = 64;          // beyond that many distinct sizes: direct DFT
 constexpr int64_t kBluesteinMinN = 128;              // below: the float64 direct DFT is cheap
-constexpr int64_t kBluesteinMaxM = 16384;            // M float2 of shared memory
+constexpr int64_t kBluesteinSmemM = 16384;           // up to here the M float2 live in shared memory
+constexpr int64_t kBluesteinMaxM = 1 << 21;          // beyond: AMC_ERR_UNSUPPORTED (frames of > 1 Mi samples)
 
 void host_fft_pow2(std::vector<std::complex<double>>& v) {
   const size_t m = v.size();
@@ -521,8 +522,10 @@ bool fused_size(int64_t n) {
   return n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096 || n == 8192 || n == 16384;
 }
 
-constexpr int64_t kGeneralPow2Max = 16384;   // N float2 of FFT scratch must fit in shared memory
-constexpr int64_t kGeneralDftMax = 12288;    // N double2 of twiddles must fit in shared memory
+constexpr int64_t kGeneralPow2Smem = 16384;  // up to here the N float2 of FFT scratch live in shared memory
+constexpr int64_t kGeneralPow2Max = 1 << 20; // beyond: AMC_ERR_UNSUPPORTED
+constexpr int64_t kGeneralDftMax = 12288;    // direct DFT: N double2 of twiddles must fit in shared memory
+constexpr size_t kFftWorkspaceMax = size_t{1} << 30;   // global FFT workspace of one launch (long frames)
 constexpr size_t kGeneralSmemMax = 200 * 1024;
 
 template <typename CT>
@@ -553,6 +556,7 @@ int launch_general(const void* iq, int64_t n_frames, int64_t n, int64_t frame_st
                    double* out, int64_t out_stride, int sms, cudaStream_t stream, int flags) {
   int fft_mode;
   size_t dyn;
+  size_t ws_elems = 0;                       // > 0: transform buffer of that many float2 per CTA in global memory
   BluesteinTables bl;
   if (is_pow2(n) && n >= 2) {
     if (n > kGeneralPow2Max)
@@ -560,18 +564,33 @@ int launch_general(const void* iq, int64_t n_frames, int64_t n, int64_t frame_st
                   (long long)kGeneralPow2Max);
     fft_mode = 1;
     dyn = static_cast<size_t>(n) * sizeof(float2);
+    if (n > kGeneralPow2Smem) {
+      ws_elems = static_cast<size_t>(n);
+      dyn = 0;
+    }
   } else {
-    if (n > kGeneralDftMax)
-      return fail(AMC_ERR_UNSUPPORTED, "non-power-of-two frame_size %lld > %lld not supported", (long long)n,
-                  (long long)kGeneralDftMax);
     int dev = 0;
     AMC_CUDA(cudaGetDevice(&dev));
-    const int rc = (flags & AMC_FLAG_DIRECT_DFT) ? AMC_OK : ensure_bluestein(dev, n, stream, &bl);
+    const bool direct = (flags & AMC_FLAG_DIRECT_DFT) != 0;
+    if (direct && n > kGeneralDftMax)
+      return fail(AMC_ERR_UNSUPPORTED, "direct DFT: frame_size %lld > %lld not supported", (long long)n,
+                  (long long)kGeneralDftMax);
+    if (!direct && n >= kBluesteinMinN && bluestein_m(n) == 0)
+      return fail(AMC_ERR_UNSUPPORTED, "non-power-of-two frame_size %lld too large (Bluestein length > %lld)",
+                  (long long)n, (long long)kBluesteinMaxM);
+    const int rc = direct ? AMC_OK : ensure_bluestein(dev, n, stream, &bl);
     if (rc != AMC_OK) return rc;
     if (bl.m > 0) {
       fft_mode = 2;
       dyn = static_cast<size_t>(bl.m) * sizeof(float2);
+      if (bl.m > kBluesteinSmemM) {
+        ws_elems = static_cast<size_t>(bl.m);
+        dyn = 0;
+      }
     } else {
+      if (n > kGeneralDftMax)
+        return fail(AMC_ERR_UNSUPPORTED, "frame_size %lld: no Bluestein tables and too long for the direct DFT",
+                    (long long)n);
       fft_mode = 0;
       dyn = static_cast<size_t>(n) * sizeof(double2);
     }
@@ -579,13 +598,27 @@ int launch_general(const void* iq, int64_t n_frames, int64_t n, int64_t frame_st
   const int cache_off = place_cache(n, fft_mode, &dyn);
   int rc = general_kernel_attr<CT>();
   if (rc != AMC_OK) return rc;
-  const int64_t cap = static_cast<int64_t>(sms) * 4;
+  int64_t cap = static_cast<int64_t>(sms) * 4;
+  float2* ws = nullptr;
+  if (ws_elems > 0) {
+    // stream-ordered workspace (cudaMallocAsync / cudaFreeAsync on the caller's stream: no synchronisation, safe
+    // between concurrent calls); the grid is trimmed so that it stays below kFftWorkspaceMax
+    const int64_t fit = static_cast<int64_t>(kFftWorkspaceMax / (ws_elems * sizeof(float2)));
+    if (cap > fit) cap = fit < 1 ? 1 : fit;
+    const int64_t ctas = n_frames < cap ? n_frames : cap;
+    AMC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), static_cast<size_t>(ctas) * ws_elems * sizeof(float2), stream));
+  }
   const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
   amc::general_features_kernel<CT><<<grid, amc::kGenThreads, dyn, stream>>>(
       static_cast<const CT*>(iq), n_frames, static_cast<int>(n), frame_stride, sample_stride, out, out_stride, fft_mode,
-      bl.chirp, bl.bfft, bl.m, cache_off, 0, 0ull);
+      bl.chirp, bl.bfft, bl.m, cache_off, 0, 0ull, ws);
   ++t_launches;
-  AMC_CUDA(cudaGetLastError());
+  cudaError_t e = cudaGetLastError();
+  if (ws) {
+    const cudaError_t e2 = cudaFreeAsync(ws, stream);
+    if (e == cudaSuccess) e = e2;
+  }
+  if (e != cudaSuccess) return fail(AMC_ERR_CUDA, "general kernel launch failed: %s", cudaGetErrorString(e));
   return AMC_OK;
 }
 
@@ -604,7 +637,7 @@ int launch_redo(const void* iq, int64_t n_frames, int64_t n, int64_t frame_strid
   const int grid = static_cast<int>(want < cap ? want : cap);
   AMC_CUDA(launch_pdl(amc::general_features_kernel<CT>, grid, amc::kGenThreads, dyn, stream, static_cast<const CT*>(iq),
                       n_frames, static_cast<int>(n), frame_stride, 1, out, out_stride, 1, nullptr, nullptr, 0, cache_off, 1,
-                      ticket));
+                      ticket, nullptr));
   ++t_launches;
   return AMC_OK;
 }
@@ -855,6 +888,17 @@ int64_t amc_workspace_bytes(int iq_dtype, int64_t n_frames, int64_t frame_size, 
   if (!is_pow2(frame_size)) {                       // Bluestein tables, cached per (device, frame_size)
     const int64_t m = bluestein_m(frame_size);
     if (m > 0) bytes += (frame_size + m) * static_cast<int64_t>(sizeof(float2));
+    if (m > kBluesteinSmemM) {                      // + the stream-ordered transform workspace of one launch
+      const int64_t per = m * static_cast<int64_t>(sizeof(float2));
+      int64_t ctas = static_cast<int64_t>(kFftWorkspaceMax) / per;
+      if (ctas < 1) ctas = 1;
+      bytes += (n_frames < ctas ? n_frames : ctas) * per;
+    }
+  } else if (frame_size > kGeneralPow2Smem) {
+    const int64_t per = frame_size * static_cast<int64_t>(sizeof(float2));
+    int64_t ctas = static_cast<int64_t>(kFftWorkspaceMax) / per;
+    if (ctas < 1) ctas = 1;
+    bytes += (n_frames < ctas ? n_frames : ctas) * per;
   }
   if (host_path) {                                  // double-buffered chunk buffers of one pipe
     const int64_t elt = iq_dtype == AMC_C128 ? 16 : 8;

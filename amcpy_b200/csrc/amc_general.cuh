@@ -112,7 +112,7 @@ __device__ __forceinline__ void general_frame(const CT* __restrict__ iq, int64_t
                                               int64_t sample_stride, double* __restrict__ out, int64_t out_stride,
                                               int fft_mode, const float2* __restrict__ bl_chirp,
                                               const float2* __restrict__ bl_bfft, int bl_m, int cache_off,
-                                              unsigned char* dyn, double* red, int tid) {
+                                              unsigned char* dyn, double* red, int tid, float2* fft_ws) {
   const bool cached = cache_off >= 0;
   double* ph_c = reinterpret_cast<double*>(dyn + (cached ? cache_off : 0));
   double* r_c = ph_c + n;
@@ -229,7 +229,8 @@ __device__ __forceinline__ void general_frame(const CT* __restrict__ iq, int64_t
   }
   double smax = 0.0;
   if (fft_mode == 1) {
-    float2* buf = reinterpret_cast<float2*>(dyn);
+    // transform buffer: shared memory, or - frames too long for it - this CTA's slice of a global workspace (L2)
+    float2* buf = fft_ws ? fft_ws : reinterpret_cast<float2*>(dyn);
     __syncthreads();                                // the phase / amplitude cache (which may alias buf) is dead now
     for (int i = tid; i < n; i += kGenThreads) {
       double a, b;
@@ -244,7 +245,7 @@ __device__ __forceinline__ void general_frame(const CT* __restrict__ iq, int64_t
     }
     __syncthreads();
   } else if (fft_mode == 2) {
-    float2* buf = reinterpret_cast<float2*>(dyn);
+    float2* buf = fft_ws ? fft_ws : reinterpret_cast<float2*>(dyn);
     __syncthreads();
     for (int i = tid; i < bl_m; i += kGenThreads) {
       float2 v = make_float2(0.0f, 0.0f);
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(kGenThreads)
 general_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int64_t frame_stride,
                         int64_t sample_stride, double* __restrict__ out, int64_t out_stride, int fft_mode,
                         const float2* __restrict__ bl_chirp, const float2* __restrict__ bl_bfft, int bl_m,
-                        int cache_off, int redo_only, unsigned long long ticket) {
+                        int cache_off, int redo_only, unsigned long long ticket, float2* fft_ws) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ double red[kGenWarps * 20];
   __shared__ int redo_rows[kGenThreads];
@@ -345,7 +346,7 @@ general_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int6
       const int cnt = redo_count;
       for (int j = 0; j < cnt; ++j) {
         general_frame<CT>(iq, r0 + redo_rows[j], n, frame_stride, sample_stride, out, out_stride, fft_mode, bl_chirp,
-                          bl_bfft, bl_m, cache_off, dyn, red, tid);
+                          bl_bfft, bl_m, cache_off, dyn, red, tid, nullptr);
         __syncthreads();
       }
     }
@@ -362,8 +363,10 @@ general_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int n, int6
     __syncthreads();
   }
   for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
+    // fft_ws: one slice of max(n, bl_m) float2 per CTA
+    float2* ws = fft_ws ? fft_ws + static_cast<size_t>(blockIdx.x) * static_cast<size_t>(fft_mode == 2 ? bl_m : n) : nullptr;
     general_frame<CT>(iq, f, n, frame_stride, sample_stride, out, out_stride, fft_mode, bl_chirp, bl_bfft, bl_m,
-                      cache_off, dyn, red, tid);
+                      cache_off, dyn, red, tid, ws);
     __syncthreads();
   }
 }

@@ -4,6 +4,8 @@ tensors at once.  torch is used for device memory and streams only."""
 
 from __future__ import annotations
 
+from contextlib import nullcontext as _nullcontext
+
 import numpy as np
 
 from . import _native as nat
@@ -89,10 +91,17 @@ def extract_features(iq, out=None, stream=None, force_general: bool = False, fea
         # fused kernel, instead of the general kernel in place (17x slower); costs a scratch copy of the batch
         x = frames_from_sample_major(x, n_frames, n, x.stride(1), stream=stream)
     if out is None:
-        out = torch.empty((n_frames, N_FEATURES), dtype=torch.float64, device=x.device)
+        # allocated on the stream the kernels run on: the caching allocator then orders any reuse of the block
+        # behind them (a block from another stream could be handed out again while the kernels are still queued)
+        with torch.cuda.stream(stream) if stream is not None else _nullcontext():
+            out = torch.empty((n_frames, N_FEATURES), dtype=torch.float64, device=x.device)
     else:
         if out.dtype != torch.float64 or not out.is_contiguous() or out.numel() != n_frames * N_FEATURES:
             raise ValueError("out must be a contiguous float64 tensor with 18 values per frame")
+        if stream is not None:
+            out.record_stream(stream)
+    if stream is not None:
+        x.record_stream(stream)          # (covers the re-layout scratch tensor, which is dropped on return)
     with torch.cuda.device(x.device):
         rc = nat.lib().amc_extract_batch(
             x.data_ptr(), _dtype_code(x), n_frames, n, x.stride(0) if n_frames > 1 else n, x.stride(1) if n > 1 else 1,
@@ -184,7 +193,10 @@ def frames_from_sample_major(src, n_frames: int, frame_size: int, sample_stride:
     """Device re-layout of a flat sample-major block (element (f, n) at f + n*sample_stride) into
     a (n_frames, frame_size) C-contiguous tensor."""
     torch = _torch()
-    dst = torch.empty((n_frames, frame_size), dtype=src.dtype, device=src.device)
+    with torch.cuda.stream(stream) if stream is not None else _nullcontext():
+        dst = torch.empty((n_frames, frame_size), dtype=src.dtype, device=src.device)
+    if stream is not None:
+        src.record_stream(stream)
     with torch.cuda.device(src.device):
         rc = nat.lib().amc_frames_from_sample_major(
             src.data_ptr(), _dtype_code(src), n_frames, frame_size, sample_stride, dst.data_ptr(), _stream_ptr(stream)

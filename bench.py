@@ -62,6 +62,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.samples = []
+        self.power = []
         self.reasons = set()
         self.max_mhz = None
         self._stop = threading.Event()
@@ -87,6 +88,10 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:  # noqa: BLE001
+                    pass
                 try:
                     r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 except Exception:  # noqa: BLE001
@@ -114,9 +119,11 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
         return {
             "sm_mhz": float(np.median(self.samples)),
+            "sm_min_mhz": int(min(self.samples)),
             "sm_max_mhz": self.max_mhz,
             "reasons": sorted(self.reasons),
             "samples": len(self.samples),
+            "power_w_max": float(max(self.power)) if self.power else None,
         }
 
 
@@ -170,6 +177,78 @@ def run_cpu_baseline(target_s: float = 12.0):
     }
 
 
+# The reference's extraction stage AS SHIPPED (feature_extraction.py:22-99): one process per modulation, each of
+# which loads the WHOLE .mat file (:46-47), takes its variable as the Fortran-ordered array loadmat returns (:48) and
+# feeds zero-copy strided views of it (:68) through an unbounded Queue to `num_threads` daemon threads (:58-61) that
+# write float32 rows (:35); the parent starts all six and joins them (:89-97).  The per-frame function is the oracle's
+# faithful restatement of calculate_features.  config.py:98 ships num_threads = 8; 1 is the GIL-free setting.
+def _shipped_worker_thread(q, fm, ids):
+    from oracle import amc_oracle as orc
+
+    while True:
+        item = q.get()
+        if item is None:
+            q.task_done()
+            return
+        sig, si, fi = item
+        with np.errstate(all="ignore"):
+            fm[si, fi, :] = orc.calculate_features_faithful(ids, sig)
+        q.task_done()
+
+
+def _shipped_process(path, key, n_snr, n_frames, frame_size, num_threads):
+    import queue
+    import threading as th
+
+    import scipy.io
+
+    parsed = scipy.io.loadmat(path)[key]                       # the whole file, once per process
+    fm = np.zeros((n_snr, n_frames, 18), dtype=np.float32)
+    q = queue.Queue()
+    ids = list(range(1, 19))
+    workers = [th.Thread(target=_shipped_worker_thread, args=(q, fm, ids), daemon=True) for _ in range(num_threads)]
+    for w in workers:
+        w.start()
+    for si in range(n_snr):
+        for fi in range(n_frames):
+            q.put((parsed[si, fi, 0:frame_size], si, fi))
+    q.join()
+    for _ in workers:
+        q.put(None)
+
+
+def run_cpu_baseline_as_shipped(frames_per_cell: int = 48):
+    import multiprocessing as mp
+    import tempfile
+
+    from amcpy_b200 import synth
+    from amcpy_b200.config import SignalConfig
+
+    info = SignalConfig().mat_info
+    res = {"kind": "port", "shape": "6 processes x num_threads threads, Fortran-order views, 6 x loadmat "
+                                    "(feature_extraction.py:42-99)",
+           "cores": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)}
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "all_modulations.mat")
+        synth.write_all_modulations_mat(path, synth.dataset(SNRS, frames_per_cell, FRAME, 31), info)
+        ctx = mp.get_context("fork")
+        frames = N_MODS * N_SNR * frames_per_cell
+        for nt in (8, 1):
+            procs = [ctx.Process(target=_shipped_process, args=(path, info[m], N_SNR, frames_per_cell, FRAME, nt))
+                     for m in synth.MODULATIONS]
+            t0 = time.perf_counter()
+            for p_ in procs:
+                p_.start()
+            for p_ in procs:
+                p_.join()
+            secs = time.perf_counter() - t0
+            ok = all(p_.exitcode == 0 for p_ in procs)
+            res[f"num_threads_{nt}"] = {"value": frames / secs if ok else None, "unit": "frames/s", "seconds": secs,
+                                        "frames": frames}
+    res["sample"] = f"{frames} frames (6x16x{frames_per_cell} of the 6x16x500x2048 c128 set) per setting"
+    return res
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -212,6 +291,164 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # the CUDA arm
 # ------------------------------------------------------------------------------------------
+CONFIG3_SNRS = [-20.0 + 2.0 * i for i in range(21)]
+CONFIG3_FRAMES = 20000          # per (modulation, SNR) cell: 6 x 21 x 20,000 = 2.52 M frames, 82.6 GB complex128
+
+
+def _kernel_source_hash() -> str:
+    """sha256 over the CUDA sources: ties committed ncu numbers (DRAM traffic) to the kernels they were taken from."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "amcpy_b200" / "csrc").glob("*.cu*")):
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def _measured_traffic():
+    """DRAM bytes per launch from the committed `ncu --set full` capture - only while the capture belongs to the
+    kernels being benchmarked (same source hash); otherwise None (a stale number is worse than none)."""
+    tf = ROOT / "profiles" / "traffic_per_launch.json"
+    try:
+        d = json.loads(tf.read_text())
+        if d.get("kernel_source_sha256_16") == _kernel_source_hash():
+            return d.get("dram_bytes_per_launch"), d.get("source")
+        return None, "profiles/traffic_per_launch.json was captured from different kernel sources: not reported"
+    except Exception:  # noqa: BLE001
+        return None, "no capture committed"
+
+
+def _timed_max_over_ranks(fn, reps, dev, dist):
+    """ms per call of `fn` (device time, CUDA events on the current stream), max over ranks."""
+    import torch
+
+    fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def strong_scaling_config3(rank, world, dev, dist, frames_per_cell=CONFIG3_FRAMES, reps=3):
+    """BASELINE config 3 (fixed total work): every rank generates and extracts a contiguous slice of the frame axis of
+    every (modulation, SNR) cell; the (2.52 M, 18) matrix gathered on rank 0 is hashed - it must not depend on N."""
+    import hashlib
+
+    import torch
+
+    from amcpy_b200 import ops, synth
+
+    if frames_per_cell % world:
+        return {"skipped": f"{frames_per_cell} frames per cell do not divide over {world} ranks"}
+    per = frames_per_cell // world
+    n_cells = N_MODS * len(CONFIG3_SNRS)
+    x = synth.dataset_device(N_MODS, CONFIG3_SNRS, per, FRAME, dev, seed=3, first_frame=rank * per)
+    out = torch.empty((x.shape[0], 18), dtype=torch.float64, device=dev)
+    ms = _timed_max_over_ranks(lambda: ops.extract_features(x, out=out), reps, dev, dist)
+    del x
+    if dist is not None:
+        parts = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+        dist.gather(out, parts, dst=0)
+    else:
+        parts = [out]
+    res = None
+    if rank == 0:
+        full = torch.stack([p_.view(n_cells, per, 18) for p_ in parts], dim=1).reshape(n_cells * frames_per_cell, 18)
+        sha = hashlib.sha256(full.cpu().numpy().tobytes()).hexdigest()
+        frames = n_cells * frames_per_cell
+        rec = ROOT / "profiles" / "config3_sha256.json"
+        want = None
+        try:
+            d = json.loads(rec.read_text())
+            if d.get("kernel_source_sha256_16") == _kernel_source_hash() and d.get("frames_per_cell") == frames_per_cell:
+                want = d.get("sha256_n1")
+        except Exception:  # noqa: BLE001
+            pass
+        res = {
+            "workload": f"BASELINE config 3: 6 mods x 21 SNR x {frames_per_cell} frames x 2048 complex128 = "
+                        f"{frames} frames, {frames * FRAME * 16 / 1e9:.1f} GB, on-device generator, fixed total work",
+            "frames": frames, "ms_per_pass": ms, "frames_per_s": frames / (ms * 1e-3),
+            "hbm_frac_per_gpu": frames * BYTES_PER_FRAME / (ms * 1e-3) / 1e9 / world / _peaks()[0],
+            "sha256_of_features": sha, "sha256_recorded_at_n1": want,
+            "matches_n1": (sha == want) if want else None, "finite": bool(torch.isfinite(full).all()),
+        }
+    del out, parts
+    torch.cuda.empty_cache()
+    return res
+
+
+def gather_timing(rank, world, dev, dist, x, n_frames):
+    """The one optional exchange of the path - the (frames, 18) matrix to the consumer's rank - both ways: NCCL
+    all_gather_into_tensor after the kernel vs the kernel's own epilogue storing rows into rank 0's matrix through
+    NVLink peer mappings (torch symmetric memory).  Every rank's shard = 1/N of this rank's bench batch."""
+    import torch
+
+    from amcpy_b200 import ops, sharding
+
+    total = (n_frames // world) * world
+    lo, hi = sharding.shard_range(total, rank, world)
+    mine = x[lo:hi]
+    res = {"frames_total": total, "rows_per_rank": hi - lo}
+    try:
+        res["extract_only_ms"] = _timed_max_over_ranks(lambda: ops.extract_features(mine), 20, dev, dist)
+        res["extract_plus_nccl_all_gather_ms"] = _timed_max_over_ranks(
+            lambda: sharding.gather_features(ops.extract_features(mine), total), 20, dev, dist)
+        a = sharding.gather_features(ops.extract_features(mine), total)
+        res["fused_peer_store_ms"] = _timed_max_over_ranks(
+            lambda: sharding.extract_sharded_to_root(mine, total, root=0), 20, dev, dist)
+        b = sharding.extract_sharded_to_root(mine, total, root=0)
+        torch.cuda.synchronize()
+        ok = torch.tensor([1 if (rank != 0 or torch.equal(a, b)) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        res["bitwise_equal"] = bool(ok.item())
+    except Exception as e:  # noqa: BLE001 - symmetric memory needs P2P access between all ranks
+        res["error"] = f"{type(e).__name__}: {str(e)[:200]}"
+    return res
+
+
+def stage_timing(dev, frames_per_cell=N_FRAMES):
+    """The drop-in stage end to end on BASELINE config 1: run_extraction(cfg) on a 1.57 GB all_modulations.mat
+    (parse + host->device + kernels + device->host + six savemat), wall clock, against the PCIe floor."""
+    import tempfile
+
+    import torch
+
+    from amcpy_b200 import synth
+    from amcpy_b200.config import Config, Paths, SignalConfig
+    from amcpy_b200.feature_extraction import run_extraction
+
+    with tempfile.TemporaryDirectory() as td:
+        cfg = Config(paths=Paths(root=Path(td)), signals=SignalConfig(num_frames=frames_per_cell))
+        cfg.paths.ensure_dirs()
+        x = synth.dataset_device(N_MODS, SNRS, frames_per_cell, FRAME, dev, seed=1).view(N_MODS, N_SNR, frames_per_cell, FRAME)
+        synth.write_all_modulations_mat(cfg.paths.mat_data / cfg.paths.mat_filename, x.cpu().numpy(), cfg.signals.mat_info)
+        del x
+        torch.cuda.empty_cache()
+        import contextlib
+        import io
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            run_extraction(cfg)                      # warm: staging buffers, page cache
+            times = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                run_extraction(cfg)
+                times.append(time.perf_counter() - t0)
+    frames = N_MODS * N_SNR * frames_per_cell
+    return {"workload": "BASELINE config 1: run_extraction on all_modulations.mat (6 x 16 x 500 x 2048 complex128, 1.57 GB)",
+            "seconds": min(times), "seconds_all": times, "frames_per_s": frames / min(times),
+            "input_gbs": frames * FRAME * 16 / min(times) / 1e9}
+
+
 def run_cuda_arm(args):
     import torch
 
@@ -247,12 +484,13 @@ def run_cuda_arm(args):
         torch.cuda.synchronize()
 
     n_frames = N_MODS * N_SNR * N_FRAMES
-    # rank-specific seed: every rank owns its own 48,000-frame batch (weak scaling)
     # hand-written on-device generator (counter-based Philox): rank r owns frames [r*500, (r+1)*500) of every cell
+    # (weak scaling: every rank streams its own 48,000-frame batch)
     x = synth.dataset_device(N_MODS, SNRS, N_FRAMES, FRAME, dev, seed=2024, first_frame=rank * N_FRAMES)
     out = torch.empty((n_frames, 18), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
     lib = nat.lib()
+    nat.check(lib.amc_init(local_rank))
 
     torch.cuda.synchronize()
     torch.cuda.profiler.start()   # no-op unless run under `ncu --profile-from-start off`
@@ -260,11 +498,12 @@ def run_cuda_arm(args):
         ops.extract_features(x, out=out)
     barrier()
 
-    # ---- device-resident timing: K launches, one CUDA-event pair per launch on the launching stream
+    # ---- device-resident timing: K steps, one CUDA-event pair per step on the launching stream
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.amc_launch_count()   # counted from here: the generator / warm-up launches are excluded
-    with ClockSampler(_physical_gpu_index(local_rank)) as clocks:
+    physical = _physical_gpu_index(local_rank)
+    with ClockSampler(physical) as clocks:
         barrier()
         t_all0.record(stream)
         for k in range(args.steps):
@@ -283,13 +522,37 @@ def run_cuda_arm(args):
     total_ms = float(t.item())
     value = world * n_frames * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end through the public host API: pinned host frames -> features on the host
     if args.no_e2e:
         if rank == 0:
             print(json.dumps({"profiling_only": True, "kernel_ms_per_launch": kernel_ms, "value": value}), flush=True)
         return 0
+
+    # ---- sustained: >= 5 s of back-to-back steps with the clock / power record (the headline run above is a burst)
+    sustained = None
+    if not args.quick:
+        with ClockSampler(physical) as sclk:
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_sus, t_host0 = 0, time.perf_counter()
+            s0.record(stream)
+            while time.perf_counter() - t_host0 < args.sustain_seconds:
+                for _ in range(200):
+                    ops.extract_features(x, out=out)
+                n_sus += 200
+                torch.cuda.synchronize()
+            s1.record(stream)
+            barrier()
+        sus_ms = torch.tensor([s0.elapsed_time(s1) / n_sus], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(sus_ms, op=dist.ReduceOp.MAX)
+        sus_ms = float(sus_ms.item())
+        sustained = {"seconds": n_sus * sus_ms * 1e-3, "steps": n_sus, "ms_per_step": sus_ms,
+                     "value": world * n_frames / (sus_ms * 1e-3), "unit": "frames/s",
+                     "hbm_frac_per_gpu": n_frames * BYTES_PER_FRAME / (sus_ms * 1e-3) / 1e9 / _peaks()[0],
+                     "clocks": sclk.summary()}
+
+    # ---- end to end through the public host API: pinned host frames -> features on the host
     # one rank per GPU: allocate (first-touch) the pinned staging buffers on the GPU's own NUMA node
-    physical = _physical_gpu_index(local_rank)
     affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
     numa_cpus = nat.bind_host_thread_to_gpu(physical)
     xh = torch.empty((n_frames, FRAME), dtype=torch.complex128, pin_memory=True)
@@ -297,32 +560,58 @@ def run_cuda_arm(args):
     oh = torch.empty((n_frames, 18), dtype=torch.float64, pin_memory=True)
     xh_np, oh_np = xh.numpy(), oh.numpy()
     e2e_steps = max(2, min(args.steps, 5))
-    ops.extract_features_host(xh_np, device=local_rank, out=oh_np)  # warm (allocates the staging buffers)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ops.extract_features_host(xh_np, device=local_rank, out=oh_np)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_frames * e2e_steps / float(te.item())
+
+    def wall_max(fn, reps):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) / reps
+
+    e2e_s = wall_max(lambda: ops.extract_features_host(xh_np, device=local_rank, out=oh_np), e2e_steps)
+    e2e_value = world * n_frames / e2e_s
     same = bool(torch.equal(torch.from_numpy(oh_np).to(dev), out))
+    # copy-only ceiling of the same transfer: the same pinned buffer to the device and the result back, no kernel,
+    # all ranks at once - what amc_extract_host could reach at best on this box at this N
+    xd_tmp = torch.empty_like(x)
+    od_tmp = torch.empty_like(out)
+
+    def copy_only():
+        xd_tmp.copy_(xh, non_blocking=True)
+        oh.copy_(od_tmp, non_blocking=True)
+        torch.cuda.synchronize()
+
+    od_tmp.copy_(out)
+    copy_s = wall_max(copy_only, e2e_steps)
+    oh.copy_(out)
+    del xd_tmp, od_tmp
+    bytes_step = n_frames * FRAME * 16 + n_frames * 18 * 8
+    # complex64 transport (captures are 8-bit / 16-bit IQ: complex64 holds them exactly): half the PCIe bytes
+    xh64 = torch.empty((n_frames, FRAME), dtype=torch.complex64, pin_memory=True)
+    xh64.copy_(x.to(torch.complex64))
+    oh64 = np.empty((n_frames, 18), dtype=np.float64)
+    e2e64_s = wall_max(lambda: ops.extract_features_host(xh64.numpy(), device=local_rank, out=oh64), e2e_steps)
+    del xh64
     if affinity0 is not None and numa_cpus:
-        os.sched_setaffinity(0, affinity0)   # the CPU baseline below uses every core of the box again
+        os.sched_setaffinity(0, affinity0)   # the CPU baselines below use every core of the box again
+
+    strong = None if args.quick else strong_scaling_config3(rank, world, dev, dist)
+    gather = gather_timing(rank, world, dev, dist, x, n_frames) if (world > 1 and not args.quick) else None
+    del xh, oh, x
+    torch.cuda.empty_cache()
+    stage = stage_timing(dev) if (world == 1 and rank == 0 and not args.quick) else None
 
     if rank == 0:
         peak, peak_src = _peaks()
         achieved = n_frames * BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        tf = ROOT / "profiles" / "traffic_per_launch.json"
-        if tf.exists():
-            try:
-                traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
-            except Exception:  # noqa: BLE001
-                traffic = None
+        traffic, traffic_src = _measured_traffic()
         cpu = run_cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
+        shipped = run_cpu_baseline_as_shipped() if (world == 1 and not args.no_cpu_baseline and not args.quick) else None
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -335,7 +624,8 @@ def run_cuda_arm(args):
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "fused16_features_kernel<2048,double2>",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": "fused16_features_kernel<2048,double2,15> (+ the careful-path scan kernel that follows it)",
                 "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": n_frames * BYTES_PER_FRAME,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
             },
@@ -344,12 +634,27 @@ def run_cuda_arm(args):
                 "d2h_bytes_per_step": n_frames * 18 * 8, "steps": e2e_steps,
                 "api": "amcpy_b200.ops.extract_features_host -> C ABI amc_extract_host (pinned host buffers)",
                 "matches_device_path": same, "host_cpus_bound": len(numa_cpus),
+                "pcie_gbs_per_gpu": bytes_step / e2e_s / 1e9,
+                "copy_only_gbs_per_gpu": bytes_step / copy_s / 1e9,
+                "frac_of_copy_only": copy_s / e2e_s,
+                "complex64_transport": {"value": world * n_frames / e2e64_s, "unit": "frames/s",
+                                        "h2d_bytes_per_step": n_frames * FRAME * 8},
             },
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
+        if sustained is not None:
+            line["sustained"] = sustained
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if gather is not None:
+            line["gather"] = gather
+        if stage is not None:
+            line["stage"] = stage
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if shipped is not None:
+            line["cpu_baseline_as_shipped"] = shipped
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -365,6 +670,8 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--quick", action="store_true", help="skip sustained / config-3 / gather / stage / as-shipped legs")
+    ap.add_argument("--sustain-seconds", type=float, default=5.0)
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 5 if args.impl == "reference" else 300

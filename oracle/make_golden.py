@@ -72,6 +72,11 @@ def main() -> None:
     if "--narrow-only" in sys.argv:
         narrow_cases()
         return
+    if "--long-only" in sys.argv:      # long frames: beyond the shared-memory FFT of the general kernel
+        for n in (12000, 32768, 65536):
+            x = np.stack([synth.frame(m, SNRS[8], 8, 0, n, SEED) for m in range(6)])
+            np.savez(GOLD / f"generic_n{n}.npz", seed=SEED, snr_idx=8, n=n, features=ref_features(x), input_sha256=sha(x))
+        return
     if "--hard-only" in sys.argv:      # leaves the other fixtures (and their zip timestamps) untouched
         hard_cases()
         return
@@ -102,7 +107,7 @@ def main() -> None:
                  features=np.stack(feats).reshape(6, len(snr_pick), 3, 18), input_sha256=sha(x))
 
     # 3. ragged / generic sizes (the reference accepts any length): one frame per class
-    for n in (10, 31, 100, 1000, 3000, 512, 8192, 16384):
+    for n in (10, 31, 100, 1000, 3000, 512, 8192, 16384, 12000, 32768, 65536):
         x = np.stack([synth.frame(m, SNRS[8], 8, 0, n, SEED) for m in range(6)])
         np.savez(GOLD / f"generic_n{n}.npz", seed=SEED, snr_idx=8, n=n,
                  features=ref_features(x), input_sha256=sha(x))

@@ -364,7 +364,8 @@ def test_c_abi_error_codes(torch_cuda):
     assert call(os=17) == -1
     assert call(mask=0) == -1
     assert call(ss=0) == -1
-    assert call(n=1 << 20, fs=1 << 20) == -2          # power of two beyond the general kernel's FFT scratch
+    assert call(n=1 << 21, fs=1 << 21) == -2          # power of two beyond the general kernel's FFT workspace limit
+    assert call(n=(1 << 20) + 1, fs=(1 << 20) + 1) == -2 and b"Bluestein" in lib.amc_last_error_string()
     assert lib.amc_extract_batch(None, nat.AMC_C128, 4, 256, 256, 1, out.data_ptr(), 18, nat.AMC_ALL_FEATURES, 0, None) == -1
     with pytest.raises(nat.AmcError):
         nat.check(call(dt=7))

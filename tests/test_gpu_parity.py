@@ -57,7 +57,7 @@ def test_general_kernel_vs_reference_golden(torch_cuda, n):
     assert_features_close(got, want)
 
 
-@pytest.mark.parametrize("n", [10, 31, 100, 1000, 3000, 512, 8192, 16384])
+@pytest.mark.parametrize("n", [10, 31, 100, 1000, 3000, 512, 8192, 16384, 12000, 32768, 65536])
 def test_ragged_and_large_frame_sizes(torch_cuda, n):
     from amcpy_b200 import ops
 

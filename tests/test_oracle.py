@@ -67,7 +67,7 @@ def test_oracle_bitwise_on_realistic_frames(n):
             assert np.array_equal(got[..., fid - 1], want[..., fid - 1]), fid
 
 
-@pytest.mark.parametrize("n", [10, 31, 100, 1000, 3000, 512, 8192, 16384])
+@pytest.mark.parametrize("n", [10, 31, 100, 1000, 3000, 512, 8192, 16384, 12000, 32768, 65536])
 def test_oracle_on_ragged_sizes(n):
     x, want = golden_generic(n)
     assert np.allclose(orc.features_batch(x), want, rtol=1e-14, atol=0)
@@ -86,6 +86,20 @@ def test_oracle_on_hard_cases_from_the_reference(n):
     assert np.isnan(want[8:]).all() and np.isnan(got[8:]).all()           # a NaN poisons all 18 features
     assert np.allclose(got[:8], want[:8], rtol=1e-13, atol=0)
     assert np.allclose(got64, want64, rtol=1e-5, atol=0)                    # float32 arithmetic in both
+
+
+@pytest.mark.parametrize("n", [256, 2048, 8192])
+def test_oracle_on_narrow_and_extreme_frames_from_the_reference(n):
+    """Narrow phase clusters, scales 1e-30 .. 1e+20, degenerate amplitude distributions (tests/golden/narrow_n*.npz)."""
+    from conftest import golden_narrow
+
+    x, want = golden_narrow(n)
+    with np.errstate(all="ignore"):
+        got = orc.features_batch(x)
+    keep = np.ones_like(want, dtype=bool)
+    keep[6, 3] = False                                   # rounding noise around an exact 0 in both (1e-16)
+    assert np.allclose(got[keep], want[keep], rtol=1e-12, atol=0)
+    assert abs(got[6, 3]) < 1e-12 and abs(want[6, 3]) < 1e-12
 
 
 def test_helpers_realistic_frame():

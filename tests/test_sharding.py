@@ -86,3 +86,86 @@ def test_consumer_semantics_without_mat_round_trip():
     assert sorted(np.bincount(yte).tolist()) == [12] * 6          # stratified
     allx = np.concatenate([xtr, xte])
     assert np.allclose(allx.mean(0), 0, atol=1e-5) and np.allclose(allx.std(0), 1, atol=1e-4)
+
+
+# ------------------------------------------------------------------ the stage's N > 1 path (gloo, CPU)
+def _fake_rows(key: str, q0: int, q1: int):
+    """Stand-in for the GPU features of frames q0..q1 of one variable: any deterministic function of (variable, q)."""
+    base = float(sum(key.encode()))
+    q = np.arange(q0, q1, dtype=np.float64)
+    return base + q[:, None] * 0.25 + np.arange(18, dtype=np.float64)[None, :] / 64.0
+
+
+def _stage_worker(rank, world, port, root, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    try:
+        import amcpy_b200._native as nat
+        import amcpy_b200.feature_extraction as fe
+        from amcpy_b200.config import Config, Paths, SignalConfig
+
+        nat.require_cuda = lambda: 1                       # host logic under test: no device in this container
+
+        def fake_planar(arr, n_snr, n_frames, frame_size, device=0, q_range=None):
+            S = arr.shape[0]
+            key = [k for k, v in fe_src.planar.items() if v is arr][0]
+            if q_range is None:
+                return fe.assemble_matrix(_fake_rows(key, 0, S * n_frames), 0, S, n_snr, n_frames)
+            return _fake_rows(key, *q_range)
+
+        cfg = Config(paths=Paths(root=Path(root)), signals=SignalConfig(num_frames=3, frame_size=64))
+        orig_init = fe._MatSource.__init__
+
+        def capture(self, *a, **k):
+            orig_init(self, *a, **k)
+            nonlocal fe_src
+            fe_src = self
+
+        fe_src = None
+        fe._MatSource.__init__ = capture
+        fe.extract_modulation_planar = fake_planar
+        res = fe.extract_all(cfg)
+        q.put((rank, sorted(res)))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_stage_shards_assemble_to_the_single_process_files_gloo(tmp_path, world):
+    """run_extraction under WORLD_SIZE ranks (gloo): contiguous shards of the flattened (modulation, frame, snr) space,
+    gathered and written by rank 0, give the files a single process writes (the GPU features replaced by a
+    deterministic stand-in: this is the host-side logic of the N > 1 path)."""
+    import scipy.io
+
+    from amcpy_b200 import synth
+    from amcpy_b200.config import Config, Paths, SignalConfig
+
+    outs = {}
+    for name, w in (("single", 1), ("sharded", world)):
+        root = tmp_path / name
+        cfg = Config(paths=Paths(root=root), signals=SignalConfig(num_frames=3, frame_size=64))
+        cfg.paths.ensure_dirs()
+        snrs = [float(v) for v in cfg.signals.snr_values.values()]
+        synth.write_all_modulations_mat(cfg.paths.mat_data / cfg.paths.mat_filename, synth.dataset(snrs, 4, 80, 3),
+                                        cfg.signals.mat_info)
+        ctx = mp.get_context("spawn")
+        qq = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_stage_worker, args=(r, w, port, str(root), qq)) for r in range(w)]
+        for p in procs:
+            p.start()
+        got = sorted(qq.get(timeout=180) for _ in procs)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        assert got[0] == (0, sorted(cfg.signals.modulations_with_noise))          # rank 0 holds every matrix
+        assert all(names == [] for _, names in got[1:])                            # the other ranks hold none
+        outs[name] = {m: scipy.io.loadmat(str(cfg.paths.calculated_features / f"{m}_features.mat"))[cfg.signals.mat_info[m]]
+                      for m in cfg.signals.modulations_with_noise}
+    for m, a in outs["single"].items():
+        assert a.shape == (16, 3, 18) and a.dtype == np.float32
+        assert np.array_equal(a, outs["sharded"][m]), m
+    a = outs["single"]["QPSK"]
+    assert a[5, 2, 0] == np.float32(_fake_rows("signal_qpsk", 5 + 16 * 2, 5 + 16 * 2 + 1)[0, 0])   # q = snr + S*frame
