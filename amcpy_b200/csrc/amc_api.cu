@@ -307,6 +307,11 @@ cudaError_t launch_pdl(void (*kern)(Params...), int grid, int block, size_t smem
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl() ? 1 : 0;
+  if (cfg.numAttrs) {   // a stream being captured into a CUDA graph gets ordinary (fully serialised) kernel nodes
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cudaGetLastError();
+    if (cap != cudaStreamCaptureStatusNone) cfg.numAttrs = 0;
+  }
   return cudaLaunchKernelEx(&cfg, kern, static_cast<Params>(args)...);
 }
 

@@ -374,70 +374,11 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
 #pragma unroll
     for (int j = 0; j < SPT; ++j) s_f += fq[j];
     }   // DO_PHASE
-#ifndef AMC_F16_SERIAL_REDUCE
-    // 16 FP64 partials per lane -> 16 warp totals, transposed through the warp-private buffer (16 STS.64 + 16 LDS.64 +
-    // 16 DADD; the shuffle butterfly needed 60 selects + 32 shuffles) - INTERLEAVED with FFT stage A: the radix-16 over
-    // this thread's own samples x[t + GROUP j] (registers) and its twiddles W_N^(t k1) are independent FP32 work that
-    // hides the shared-memory round trip and the dependent FP64 adds of the reduction (it was 11 % of the warp time
-    // at 6.6 stall samples per instruction, profiles/r1p); everything up to the rbar wait is one basic block.
-    float2 v[16];
-    const int tv = opaque_if<Cfg::REG_BOUND>(t);          // keeps the geometry below out of pass 1
-    const int lv = tv & 31, wv = tv >> 5;
-    {
-      double* red = reinterpret_cast<double*>(tbuf);
-      __syncwarp();                                     // stage C of the previous frame has read tbuf
-#pragma unroll
-      for (int i = 0; i < 15; ++i) red[lane * kTRow + i] = mono.s[i];
-      red[lane * kTRow + 15] = sum_r;
-      float accf[4] = {s_ph, s_aph, s_f, 0.0f};
-      warp_sum_multi<float, 4>(accf, lane);
-      __syncwarp();
-      float4 tw[8];
-      if constexpr (DO_FFT) {
-#pragma unroll
-        for (int p = 0; p < 8; ++p) tw[p] = g_tw_a4[tw_a4_offset(N) + p * GROUP + tv];            // 512 B per warp load
-      }
-      const double* col = red + (lane >> 4) * (16 * kTRow) + (lane & 15);
-      double cs[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) cs[i] = col[i * kTRow];
-      if constexpr (DO_FFT) {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = make_float2(xr[q], xi[q]);
-        dft16(v);
-      }
-#pragma unroll
-      for (int w = 8; w >= 1; w >>= 1)                  // pairwise tree: same error growth as the butterfly
-#pragma unroll
-        for (int i = 0; i < w; ++i) cs[i] += cs[i + w];
-      const double tot = cs[0] + __shfl_xor_sync(0xffffffffu, cs[0], 16);
-      if constexpr (DO_FFT) {
-#pragma unroll
-        for (int q = 1; q < 16; ++q) {
-          const float4 w = tw[(q - 1) >> 1];
-          v[bitrev4(q)] = c_mul(v[bitrev4(q)], (q & 1) ? make_float2(w.x, w.y) : make_float2(w.z, w.w));
-        }
-      }
-      // every warp has finished reading the previous frame's stage-A output and (warp 0) the partials
-      // that are about to be overwritten; in steady state this completed long ago
-      mbar_wait(rbar, static_cast<uint32_t>(par));
-      if (lane < 16) part_d(par, wg)[lane] = tot;
-      if ((lane & 7) == 0 && lane < 24) part_f(par, wg)[lane >> 3] = accf[0];
-      if (lane == 16) part_d(par, wg)[23] = static_cast<double>(accf[0]);   // sum f, again, for the finalisation
-      if constexpr (DO_FFT) {
-        const int rot_t = (((tv & 15) << (4 - LOG_M1)) | ((tv & 15) >> LOG_M1)) & 15;
-        const uint32_t row_a = (smem_u32(buf_a) + 128u * tv) ^ (8u * rot_t);   // row start is 128-byte aligned
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {   // element (t, q) -> row t, slot q ^ rot_t
-          const float2 o = v[bitrev4(q)];
-          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(row_a ^ (8u * q)), "f"(o.x), "f"(o.y) : "memory");
-        }
-      }
-    }
-#else
     {
       // 16 FP64 partials per lane -> 16 warp totals: transposed through the warp-private buffer
-      // (16 STS.64 + 16 LDS.64 + 16 DADD; the shuffle butterfly needed 60 selects + 32 shuffles)
+      // (16 STS.64 + 16 LDS.64 + 16 DADD; the shuffle butterfly needed 60 selects + 32 shuffles).
+      // (Interleaving this shared-memory round trip with the register-only radix-16 of stage A in one basic block was
+      //  measured in round 2: 0.6321 vs 0.6279 ms - slower; profiles/r2_experiments.txt.)
       double* red = reinterpret_cast<double*>(tbuf);
       __syncwarp();                                     // stage C of the previous frame has read tbuf
 #pragma unroll
@@ -503,8 +444,6 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(row_a ^ (8u * q)), "f"(o.x), "f"(o.y) : "memory");
       }
     }
-
-#endif
 
     group_sync<GROUP, Cfg::CTA>(g);   // THE barrier: pass-1 partials + stage-A output visible; x slot fully read
 

@@ -437,3 +437,48 @@ def test_device_consumer_matches_host_consumer(torch_cuda):
     xtr, xte, ytr, yte = stratified_split_device(xs, yd, cfg.training.test_size, cfg.training.random_state)
     assert xtr.shape[0] + xte.shape[0] == xs.shape[0] and xte.shape[0] == 6 * round(0.2 * 72)
     assert torch_cuda.bincount(yte).tolist() == [round(0.2 * 72)] * 6
+
+
+def test_cuda_graph_capture_and_replay(torch_cuda):
+    """amc_init builds the tables eagerly, after which amc_extract_batch only enqueues kernels: the call can be captured
+    into a CUDA graph (launch-bound small batches) and replayed on new data in the same buffers."""
+    from amcpy_b200 import _native as nat
+    from amcpy_b200 import ops, synth
+
+    nat.check(nat.lib().amc_init(0))
+    snrs = [0.0, 10.0]
+    x = synth.dataset_device(6, snrs, 4, 1024, torch_cuda.device("cuda"), seed=1)
+    out = torch_cuda.empty((x.shape[0], 18), dtype=torch_cuda.float64, device="cuda")
+    want1 = ops.extract_features(x).clone()
+    s = torch_cuda.cuda.Stream()
+    s.wait_stream(torch_cuda.cuda.current_stream())
+    g = torch_cuda.cuda.CUDAGraph()
+    with torch_cuda.cuda.stream(s):
+        ops.extract_features(x, out=out, stream=s)          # warm-up on the capture stream
+        s.synchronize()
+        with torch_cuda.cuda.graph(g, stream=s):
+            ops.extract_features(x, out=out, stream=s)
+    out.zero_()
+    g.replay()
+    torch_cuda.cuda.synchronize()
+    assert torch_cuda.equal(out, want1)
+    x.copy_(synth.dataset_device(6, snrs, 4, 1024, torch_cuda.device("cuda"), seed=2))
+    want2 = ops.extract_features(x).clone()
+    g.replay()
+    torch_cuda.cuda.synchronize()
+    assert torch_cuda.equal(out, want2) and not torch_cuda.equal(want1, want2)
+
+
+def test_concurrent_host_calls_share_a_device(torch_cuda):
+    """Four host threads call amc_extract_host on the same device at once: each takes its own copy/compute pipe of the
+    library (amc_api.cu: HostPipe pool); results are bitwise what a single call returns."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from amcpy_b200 import ops, synth
+
+    rng_sets = [np.concatenate([synth.cell(m, 6.0, 8, range(40), 2048, seed=50 + k) for m in range(6)]) for k in range(6)]
+    want = [ops.extract_features_host(a) for a in rng_sets]
+    with ThreadPoolExecutor(max_workers=6) as pool:          # more threads than pipes: two of them queue
+        got = list(pool.map(ops.extract_features_host, rng_sets))
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)

@@ -1,0 +1,15 @@
+# ncu evidence of the round (one gpurun call; each command has exited 0 without ncu first - gpurun checks that itself):
+#  1. launch list of the benchmark command (shares of the step, cold-cache serialised times)
+#  2. --set full capture of the hot kernel (source page: compiled with -lineinfo)
+#  3. --set full capture of one launch of every shipped kernel family (tools/profile_families.py)
+set -x
+python bench.py --no-e2e --steps 20 --warmup 3 > gpurun_out/r2_plain.json 2> gpurun_out/r2_plain.err &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r2_launches.csv \
+    python bench.py --no-e2e --steps 20 --warmup 3 > gpurun_out/r2_ncu1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:fused16_features -s 5 -c 1 -f -o gpurun_out/r2_prof_fused16 \
+    python bench.py --no-e2e --steps 8 --warmup 3 > gpurun_out/r2_ncu2.log 2>&1
+python tools/profile_families.py > gpurun_out/r2_families_plain.jsonl 2> gpurun_out/r2_families_plain.err &&
+ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/r2_families \
+    python tools/profile_families.py > gpurun_out/r2_ncu3.log 2>&1
+python bench.py > gpurun_out/r2e_bench.json 2> gpurun_out/r2e_bench.err
+python tools/sweep.py --steps 30 > gpurun_out/r2e_sweep.jsonl 2>&1
