@@ -20,6 +20,9 @@
 #include "amc_fused.cuh"
 #include "amc_fused16.cuh"
 #include "amc_fusedw.cuh"
+#ifdef AMC_F16_V2
+#include "experiments/amc_fused16x.cuh"   // N = 2048 at four CTAs per SM: correct, 13 % slower (profiles/r2_experiments.txt)
+#endif
 #ifdef AMC_EXPERIMENTS
 #include "experiments/amc_fusedws.cuh"
 #endif
@@ -31,6 +34,7 @@ namespace {
 
 thread_local std::string t_err;
 thread_local int64_t t_launches = 0;
+thread_local bool t_allow_pdl = true;   // set per call by amc_extract_batch (see there)
 std::atomic<unsigned long long> g_ticket{1};   // unique, increasing id of every fused launch (amc_device.cuh: g_redo_ring)
 
 int fail(int code, const char* fmt, ...) {
@@ -306,7 +310,7 @@ cudaError_t launch_pdl(void (*kern)(Params...), int grid, int block, size_t smem
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cfg.numAttrs = (use_pdl() && t_allow_pdl) ? 1 : 0;
   if (cfg.numAttrs) {   // a stream being captured into a CUDA graph gets ordinary (fully serialised) kernel nodes
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cudaGetLastError();
@@ -381,6 +385,32 @@ int launch_fused16(const void* iq, int64_t n_frames, int64_t frame_stride, doubl
   ++t_launches;
   return AMC_OK;
 }
+
+#ifdef AMC_F16_V2
+// N = 2048, four CTAs per SM (experiments/amc_fused16x.cuh)
+template <typename CT>
+int launch_fused16x(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride,
+                    int sms, cudaStream_t stream, unsigned long long ticket) {
+  using Cfg = amc::Fused16xCfg<CT>;
+  auto kern = amc::fused16x_features_kernel<CT>;
+  static thread_local int blocks_per_sm[kMaxDevices] = {};
+  int dev = 0;
+  AMC_CUDA(cudaGetDevice(&dev));
+  if (blocks_per_sm[dev] == 0) {
+    AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int occ = 0;
+    AMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::CTA, Cfg::SMEM_BYTES));
+    if (occ < 1) return fail(AMC_ERR_CUDA, "fused16x kernel does not fit on this device");
+    blocks_per_sm[dev] = occ;
+  }
+  const int64_t cap = static_cast<int64_t>(sms) * blocks_per_sm[dev];
+  const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
+  AMC_CUDA(launch_pdl(kern, grid, Cfg::CTA, Cfg::SMEM_BYTES, stream, static_cast<const CT*>(iq), n_frames, frame_stride,
+                      out, out_stride, ticket));
+  ++t_launches;
+  return AMC_OK;
+}
+#endif  // AMC_F16_V2
 
 #ifdef AMC_EXPERIMENTS
 template <int N, typename CT>
@@ -511,6 +541,9 @@ int dispatch_fused(int64_t n, const void* iq, int64_t n_frames, int64_t frame_st
       default: break;
     }
   }
+#ifdef AMC_F16_V2
+  if (n == 2048) return launch_fused16x<CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
+#endif
   switch (n) {
     case 256: return launch_fusedw<256, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
     case 512: return launch_fused16<512, CT>(iq, n_frames, frame_stride, out, out_stride, sms, stream, ticket);
@@ -941,6 +974,10 @@ int amc_extract_batch(const void* iq, int iq_dtype, int64_t n_frames, int64_t fr
     const int prof = pick_profile(feature_mask);
     int used = amc::kProfAll;
     const unsigned long long ticket = g_ticket.fetch_add(1, std::memory_order_relaxed);
+    // Programmatic dependent launch is worth 0.3-0.6 % of a step at every fused size except N = 1024, whose
+    // 64-thread CTAs (four per SM) lose 10 % when the successor's CTAs become resident during the tail
+    // (profiles/r2_experiments.txt): that size gets ordinary launches.
+    t_allow_pdl = frame_size != 1024;
     if (iq_dtype == AMC_C128)
       rc = dispatch_fused<double2>(frame_size, iq, n_frames, frame_stride, out, out_stride, di.sms, stream, flags, prof,
                                    &used, ticket);

@@ -314,6 +314,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 constexpr int kCheckRange = 1, kCheckPhase = 2, kCheckAmp = 4;
 constexpr int kCheckAll = 7;
+constexpr int kCheckForce = 8;              // the kernel itself found the frame outside its fast path (amc_fused16x.cuh)
 constexpr double kNarrowRad = 0.1;          // rad; below it the careful path takes over
 
 // Writes the 18 features (column k = feature id k+1, features.py:192-211).
@@ -326,7 +327,7 @@ __device__ __noinline__ bool finalize_features(const FrameSums& fs, int n, doubl
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   const double pw = (fs.mono[0] + fs.mono[1]) * inv_n;               // mean |x|^2
   if (checks != 0 && n >= 2 && pw == pw) {                           // (NaN frames stay on the NaN rule below)
-    bool redo = false;
+    bool redo = (checks & kCheckForce) != 0;
     if (checks & kCheckRange) {
       const double hi = 1.2089258196146292e+24 * (2048.0 * inv_n);   // 2^80 * 2048/N: N^2 * sum|x|^2 stays < 2^126
       redo = redo || !(pw >= 7.888609052210118e-31 && pw <= hi);     // 2^-100; also catches +inf and an all-zero frame

@@ -1,7 +1,8 @@
 # ncu evidence of the round (one gpurun call; each command has exited 0 without ncu first - gpurun checks that itself):
 #  1. launch list of the benchmark command (shares of the step, cold-cache serialised times)
-#  2. --set full capture of the hot kernel (source page: compiled with -lineinfo)
-#  3. --set full capture of one launch of every shipped kernel family (tools/profile_families.py)
+#  2. --set full capture of the hot kernel (source page: compiled with -lineinfo); the report comes back (~17 MB)
+#  3. --set full capture of one launch of every shipped kernel family (tools/profile_families.py); the report stays on
+#     the box (hundreds of MB), only its summaries come back
 set -x
 python bench.py --no-e2e --steps 20 --warmup 3 > gpurun_out/r2_plain.json 2> gpurun_out/r2_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r2_launches.csv \
@@ -9,7 +10,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file
 ncu --set full --clock-control none --import-source on -k regex:fused16_features -s 5 -c 1 -f -o gpurun_out/r2_prof_fused16 \
     python bench.py --no-e2e --steps 8 --warmup 3 > gpurun_out/r2_ncu2.log 2>&1
 python tools/profile_families.py > gpurun_out/r2_families_plain.jsonl 2> gpurun_out/r2_families_plain.err &&
-ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/r2_families \
+ncu --set full --clock-control none --profile-from-start off -f -o /tmp/r2_families \
     python tools/profile_families.py > gpurun_out/r2_ncu3.log 2>&1
+python tools/ncu_summary.py /tmp/r2_families.ncu-rep > gpurun_out/r2_families_summary.txt 2>&1
+ls -la /tmp/r2_families.ncu-rep gpurun_out >> gpurun_out/r2_ncu3.log
 python bench.py > gpurun_out/r2e_bench.json 2> gpurun_out/r2e_bench.err
 python tools/sweep.py --steps 30 > gpurun_out/r2e_sweep.jsonl 2>&1
+du -sh gpurun_out >> gpurun_out/r2_ncu3.log
