@@ -466,19 +466,37 @@ template <int N, typename CT>
 int launch_large(const void* iq, int64_t n_frames, int64_t frame_stride, double* out, int64_t out_stride, int sms,
                  cudaStream_t stream, unsigned long long ticket) {
   using Cfg = amc::LargeCfg<N>;
-  auto kern = amc::large_features_kernel<N, CT>;
+  auto kern = amc::large_features_kernel<N, CT, true>;
+  auto kern_plain = amc::large_features_kernel<N, CT, false>;
   static thread_local bool attr_set[kMaxDevices] = {};
   int dev = 0;
   AMC_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev]) {   // once per (thread, device), not on every launch
     AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    AMC_CUDA(cudaFuncSetAttribute(kern_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set[dev] = true;
   }
   const int64_t cap = static_cast<int64_t>(sms) * Cfg::MIN_BLOCKS;
   const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
-  AMC_CUDA(launch_pdl(kern, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, static_cast<const CT*>(iq), n_frames,
-                      frame_stride, out, out_stride, ticket));
+  // |x| scratch: N doubles per CTA from the stream-ordered pool (no synchronisation); without it the kernel recomputes
+  double* ws = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&ws), static_cast<size_t>(grid) * N * sizeof(double), stream) != cudaSuccess) {
+    cudaGetLastError();
+    ws = nullptr;
+  }
+  cudaError_t e;
+  if (ws)
+    e = launch_pdl(kern, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, static_cast<const CT*>(iq), n_frames, frame_stride,
+                   out, out_stride, ticket, ws);
+  else
+    e = launch_pdl(kern_plain, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, static_cast<const CT*>(iq), n_frames,
+                   frame_stride, out, out_stride, ticket, static_cast<double*>(nullptr));
   ++t_launches;
+  if (ws) {
+    const cudaError_t e2 = cudaFreeAsync(ws, stream);
+    if (e == cudaSuccess) e = e2;
+  }
+  if (e != cudaSuccess) return fail(AMC_ERR_CUDA, "long-frame kernel launch failed: %s", cudaGetErrorString(e));
   return AMC_OK;
 }
 

@@ -1,12 +1,17 @@
 // Long frames (N = 8192, 16384): one 512-thread CTA per frame, persistent over frames.
 // The frame does not fit the "registers hold the whole frame" scheme of the fused kernels, so:
-//   pass 1 streams x from HBM (coalesced 16-byte loads): FP64 monomials + |x|, FP32 atan2; the
-//          FP32 copy of x goes to the FFT buffer and the phase to a phase buffer, both in shared memory;
-//   pass 1b forms the wrapped phase differences from the phase buffer (FP64 re-decision of ties);
-//   pass 2 re-reads x (L2-resident: 148 CTAs x 256 KB < L2) for the centred amplitude sums and the
-//          phase buffer for the centred phase / frequency sums;
+//   pass 1 streams x from HBM (coalesced 16-byte loads): FP64 monomials + |x| (stashed in an L2-resident scratch),
+//          FP32 atan2 and the raw power sums of phi and |phi| - pi/2; the FP32 copy of x goes to the FFT buffer and
+//          the phase to a phase buffer, both in shared memory;
+//   pass 1b forms the wrapped phase differences from the phase buffer (FP64 re-decision of ties) and their raw power
+//          sums (sum f .. sum f^4);
+//   pass 2 reads |x| back for the centred amplitude sums (the only statistics that need the mean first);
 //   FFT    in-place Stockham, radix 16 x 16 x 16 x (N/4096), XOR-swizzled, lane-contiguous twiddle tables.
-// Same numerics / tolerances as the fused kernels.
+// Phase / frequency statistics are ONE-PASS (round 2: raw float32 sums centred in float64 at finalisation; a frame whose
+// cancellation factor exceeds 4, or whose frequency mean exceeds 0.4 sigma, goes to the careful path) - the two-pass
+// form cost a second trip through the phase buffer and a second evaluation of every wrapped difference:
+// N = 8192 / 16384: 27.8 / 26.6 % -> 29.1 / 28.5 % of the measured HBM peak; with the |x| stash see profiles/r2_experiments.txt.
+// Same tolerance classes as the fused kernels.
 #pragma once
 #include "amc_fused16.cuh"
 
@@ -36,7 +41,7 @@ struct LargeCfg {
   static constexpr int PHI_BYTES = N * 4;
   static constexpr int PART_BYTES = 2 * WARPS * 32 * 8;            // two parities x warps x 32 doubles
   static constexpr int BATCH = 32;                                 // frames finalised together, one lane each
-  static constexpr int PEND_STRIDE = 25;                           // doubles per parked frame (odd: conflict-free)
+  static constexpr int PEND_STRIDE = 29;                           // 28 parked values per frame (odd stride: conflict-free)
   static constexpr int PEND_BYTES = BATCH * PEND_STRIDE * 8;
   static constexpr int SMEM_BYTES = FFT_BYTES + PHI_BYTES + PART_BYTES + PEND_BYTES + 64;
   static constexpr int R4 = N / 4096;                              // radix of the last stage
@@ -119,10 +124,13 @@ __device__ __forceinline__ void large_stage16(float2* __restrict__ buf, const fl
   __syncthreads();
 }
 
-template <int N, typename CT>
+// STASH: |x| of every sample is written to this CTA's slice of a global scratch (`r_ws`, N doubles per CTA: 19 MB for
+// the whole grid, L2-resident) in pass 1 and read back in pass 2, instead of re-reading x and recomputing the square
+// root there (5 FP64 operations + 4 integer / MUFU per sample).
+template <int N, typename CT, bool STASH>
 __global__ void __launch_bounds__(LargeCfg<N>::THREADS, LargeCfg<N>::MIN_BLOCKS)
 large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame_stride,
-                      double* __restrict__ out, int64_t out_stride, unsigned long long ticket) {
+                      double* __restrict__ out, int64_t out_stride, unsigned long long ticket, double* __restrict__ r_ws) {
   pdl_launch_dependents();   // the careful-path kernel may be launched now; it waits for this grid to complete
   using Cfg = LargeCfg<N>;
   constexpr int THREADS = Cfg::THREADS, WARPS = Cfg::WARPS;
@@ -146,6 +154,9 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     mono.clear();
     double sum_r = 0.0;
     float s_ph = 0.0f, s_aph = 0.0f;
+    // one-pass phase statistics (round 2): raw power sums of phi and of t = |phi| - pi/2 (s_aph holds sum t), centred in
+    // float64 when the frame is finalised; the careful path takes frames whose cancellation factor exceeds 4
+    float s_p2 = 0.0f, s_t2 = 0.0f;
     // software-pipelined with two register buffers (ping-pong, no loop-carried moves): the 16-byte loads of
     // the next group are issued before the current group is processed (ncu: 32 % of the stall samples
     // were long-scoreboard waits on these loads)
@@ -155,6 +166,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
         for (int u = 0; u < kLargeU; ++u) g[u] = x[i0 + THREADS * u];
       };
       float2* buf_t = buf + (tid ^ ((tid >> 4) & 15));      // swizzled position of sample tid (+ multiples of THREADS)
+      [[maybe_unused]] double* r_mine = STASH ? r_ws + static_cast<size_t>(blockIdx.x) * N : nullptr;
       auto pass1_group = [&](const CT (&g)[kLargeU], int i0) {
 #pragma unroll
         for (int u = 0; u < kLargeU; ++u) {
@@ -163,12 +175,17 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
           float af, bf;
           split_sample(g[u], a, b, af, bf);
           const double s = mono.add(a, b);
-          sum_r += sqrt_nr(s);
+          const double rr = sqrt_nr(s);
+          sum_r += rr;
+          if constexpr (STASH) r_mine[i] = rr;
           const float p = atan2_fast(bf, af);
           buf_t[i - tid] = make_float2(af, bf);           // = buf[swz16(i)]: (i >> 4) & 15 == (tid >> 4) & 15
           phi[i] = p;
           s_ph += p;
-          s_aph += fabsf(p);
+          const float tt = fabsf(p) - kPiO2F;
+          s_aph += tt;
+          s_p2 = fmaf(p, p, s_p2);
+          s_t2 = fmaf(tt, tt, s_t2);
         }
       };
       constexpr int STEP = THREADS * kLargeU;               // samples per group over the whole CTA
@@ -187,6 +204,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     __syncthreads();
     // ---------------------------------------------------------------- pass 1b: sum of wrapped differences
     float s_f = 0.0f;
+    float s_f2 = 0.0f, s_f3 = 0.0f, s_f4 = 0.0f;            // one-pass frequency statistics (cycles per sample)
 #pragma unroll 4
     for (int i = tid; i < N - 1; i += THREADS) {
       float dd = phi[i + 1] - phi[i];
@@ -199,6 +217,10 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
         fj = dd * kInvTwoPiF;
       }
       s_f += fj;
+      const float f2 = fj * fj;
+      s_f2 += f2;
+      s_f3 = fmaf(f2, fj, s_f3);
+      s_f4 = fmaf(f2, f2, s_f4);
     }
     {
       double acc[16];
@@ -206,62 +228,52 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
       for (int i = 0; i < 15; ++i) acc[i] = mono.s[i];
       acc[15] = sum_r;
       warp_sum_multi<double, 16>(acc, lane);
-      float accf[4] = {s_ph, s_aph, s_f, 0.0f};
-      warp_sum_multi<float, 4>(accf, lane);
       if ((lane & 1) == 0) pw[lane >> 1] = acc[0];                          // 0..15
-      if ((lane & 7) == 0) pw[16 + (lane >> 3)] = static_cast<double>(accf[0]);   // 16..19
+      float accf[8] = {s_p2, s_t2, s_f2, s_f4, s_f, s_ph, s_aph, s_f3};
+      warp_sum_multi<float, 8>(accf, lane);
+      if ((lane & 3) == 0) pw[16 + (lane >> 2)] = static_cast<double>(accf[0]);   // 16..23
     }
     __syncthreads();
-    double tot_r = 0.0, tot_ph = 0.0, tot_aph = 0.0, tot_f = 0.0;
+    double tot_r = 0.0;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) {
-      tot_r += pall[w * 32 + 15];
-      tot_ph += pall[w * 32 + 16];
-      tot_aph += pall[w * 32 + 17];
-      tot_f += pall[w * 32 + 18];
-    }
+    for (int w = 0; w < WARPS; ++w) tot_r += pall[w * 32 + 15];
     const double mu_r = tot_r * (1.0 / N);
-    const float mu_ph = static_cast<float>(tot_ph * (1.0 / N)), mu_aph = static_cast<float>(tot_aph * (1.0 / N));
-    const float mu_f = static_cast<float>(tot_f * (1.0 / (N - 1)));
 
     // ---------------------------------------------------------------- pass 2: centred sums
     double c2acc[4] = {0.0, 0.0, 0.0, 0.0};
-    float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    {                                                          // same software pipeline (L2-resident re-read)
-      auto load_group = [&](CT (&g)[kLargeU], int i0) {
+    if constexpr (STASH) {                                     // |x| comes back from the L2-resident scratch
+      const double* r_mine = r_ws + static_cast<size_t>(blockIdx.x) * N;
+      constexpr int U2 = 8;
+      static_assert(N % (THREADS * U2) == 0, "stash read loop");
+#pragma unroll 1
+      for (int i0 = tid; i0 < N; i0 += THREADS * U2) {
+        double rv[U2];
 #pragma unroll
-        for (int u = 0; u < kLargeU; ++u) g[u] = x[i0 + THREADS * u];
-      };
-      auto pass2_group = [&](const CT (&g)[kLargeU], int i0) {
+        for (int u = 0; u < U2; ++u) rv[u] = r_mine[i0 + THREADS * u];
 #pragma unroll
-        for (int u = 0; u < kLargeU; ++u) {
-          const int i = i0 + THREADS * u;
-          const double a = static_cast<double>(g[u].x), b = static_cast<double>(g[u].y);
-          const double d = sqrt_nr(fma(a, a, b * b)) - mu_r;
+        for (int u = 0; u < U2; ++u) {
+          const double d = rv[u] - mu_r;
           const double d2 = d * d;
           c2acc[0] += fabs(d);
           c2acc[1] += d2;
           c2acc[2] = fma(d2, d2, c2acc[2]);
-          const float p = phi[i];
-          const float e = p - mu_ph;
-          q2acc[0] = fmaf(e, e, q2acc[0]);
-          const float ea = fabsf(p) - mu_aph;
-          q2acc[1] = fmaf(ea, ea, q2acc[1]);
-          if (i < N - 1) {
-            float dd = phi[i + 1] - p;
-            const float over = fabsf(dd) - kPiF;
-            float fj;
-            if (fabsf(over) < kTieEps) {
-              fj = exact_freq_step<CT>(x, i);
-            } else {
-              if (over > 0.0f) dd -= copysignf(kTwoPiF, dd);
-              fj = dd * kInvTwoPiF;
-            }
-            const float ef = fj - mu_f;
-            const float ef2 = ef * ef;
-            q2acc[2] += ef2;
-            q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
-          }
+        }
+      }
+    } else {                                                   // no scratch: re-read x (L2-resident), same software pipeline
+      auto load_group = [&](CT (&g)[kLargeU], int i0) {
+#pragma unroll
+        for (int u = 0; u < kLargeU; ++u) g[u] = x[i0 + THREADS * u];
+      };
+      auto pass2_group = [&](const CT (&g)[kLargeU]) {
+#pragma unroll
+        for (int u = 0; u < kLargeU; ++u) {
+          const double a = static_cast<double>(g[u].x), b = static_cast<double>(g[u].y);
+          // |x|^2 formed exactly as Monomials::add forms it in pass 1: the same bits as the stashed values
+          const double d = sqrt_nr(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b))) - mu_r;
+          const double d2 = d * d;
+          c2acc[0] += fabs(d);
+          c2acc[1] += d2;
+          c2acc[2] = fma(d2, d2, c2acc[2]);
         }
       };
       constexpr int STEP = THREADS * kLargeU;
@@ -270,17 +282,13 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
 #pragma unroll 1
       for (int i0 = tid; i0 < N; i0 += 2 * STEP) {
         load_group(gb, i0 + STEP);
-        pass2_group(ga, i0);
+        pass2_group(ga);
         if (i0 + 2 * STEP < N) load_group(ga, i0 + 2 * STEP);
-        pass2_group(gb, i0 + STEP);
+        pass2_group(gb);
       }
     }
     warp_sum_multi<double, 4>(c2acc, lane);
-    warp_sum_multi<float, 4>(q2acc, lane);
-    if ((lane & 7) == 0) {
-      pw[20 + (lane >> 3)] = c2acc[0];                                   // 20..23 (23 unused)
-      pw[24 + (lane >> 3)] = static_cast<double>(q2acc[0]);              // 24..27
-    }
+    if ((lane & 7) == 0) pw[24 + (lane >> 3)] = c2acc[0];                // 24..27 (27 unused)
 
     // ---------------------------------------------------------------- FFT: 16 x 16 x 16 x R4, in place
     large_stage16<N, 1, Cfg::BPT, THREADS>(buf, nullptr, tid);
@@ -316,9 +324,11 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
       // other 15 warps waiting at the next frame's first barrier for 17 % of their time (latency-bound FP64 chain)
       const int bi = it % Cfg::BATCH;
       double* pe = pend + bi * Cfg::PEND_STRIDE;
-      // slot of value i in the per-warp partial rows: 0..15 | 18 (sum f) | 20,21,22 | 24..27 | 28 (max)
-      if (lane < 25) {
-        const int src = lane < 16 ? lane : (lane < 19 ? lane + 4 : (lane < 23 ? lane + 5 : (lane == 23 ? 18 : 28)));
+      // parked values: 0..15 FP64 sums, 16..18 centred amplitude sums, 19 sum phi^2, 20 sum t^2, 21 sum f^2, 22 sum f^4,
+      // 23 sum f, 24 max, 25 sum phi, 26 sum t, 27 sum f^3; partial rows: 0..15 | 16..23 float sums | 24..26 | 28 (max)
+      constexpr int kParked = 28;
+      if (lane < kParked) {
+        const int src = lane < 16 ? lane : (lane < 19 ? lane + 8 : (lane < 24 ? lane - 3 : (lane == 24 ? 28 : lane - 4)));
         double v = pall[src];
         if (lane == 24) {
 #pragma unroll
@@ -340,14 +350,22 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
           fs.c_abs1 = pl[16];
           fs.c2 = pl[17];
           fs.c4 = pl[18];
-          fs.ph_m2 = pl[19];
-          fs.aph_m2 = pl[20];
-          fs.f_m2 = pl[21];
-          fs.f_m4 = pl[22];
-          fs.mean_f = pl[23] / (N - 1);
           fs.spec_max = pl[24];
+          int checks = kCheckAll;
+          {   // centre the one-pass sums in float64 (frequency in cycles per sample)
+            constexpr double dn = N, n1 = N - 1;
+            const double mu_f = pl[23] / n1;
+            fs.ph_m2 = pl[19] - pl[25] * pl[25] / dn;
+            fs.aph_m2 = pl[20] - pl[26] * pl[26] / dn;
+            fs.f_m2 = pl[21] - pl[23] * mu_f;
+            fs.f_m4 = pl[22] - 4.0 * mu_f * pl[27] + 6.0 * mu_f * mu_f * pl[21] - 3.0 * n1 * mu_f * mu_f * mu_f * mu_f;
+            fs.mean_f = mu_f;
+            // cancellation factor of the float32 raw sums <= 4, frequency mean small against its spread
+            if (!(pl[19] <= 4.0 * fs.ph_m2) || !(pl[20] <= 4.0 * fs.aph_m2) || !(mu_f * mu_f * n1 <= 0.16 * fs.f_m2))
+              checks |= kCheckForce;
+          }
           const int64_t fo = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it - bi + lane) * gridDim.x;
-          finalize_features(fs, N, out + fo * out_stride, kCheckAll, ticket);
+          finalize_features(fs, N, out + fo * out_stride, checks, ticket);
         }
         __syncwarp();
       }
