@@ -16,7 +16,16 @@
 //     and finalises 32 frames at once, one lane per frame, instead of 32 redundant lanes per frame;
 //   * only ONE block barrier per frame: stage A is written before the pass-1 barrier, the x slot is
 //     refilled by TMA right after that barrier, everything after it is warp-local, and a frame's
-//     totals are collected one frame later (double-buffered partials).
+//     totals are collected one frame later (double-buffered partials);
+//   * (round 2) phase / |phase| / frequency statistics are ONE-PASS: pass 1 accumulates raw float32 power sums
+//     (sum phi, sum phi^2, sum t, sum t^2 with t = |phi| - pi/2, sum f .. sum f^4 of the unwrapped phase steps), the
+//     wrapped difference of a sample is formed in the iteration that computes its phase, and the sums are centred in
+//     float64 when the frame is finalised - ph[16] and fq[16] no longer live across the barrier (165 registers, no
+//     spills, -4 % instructions, 0.6287 -> 0.6079 ms).  Raw sums cancel when |mean| is large against the spread:
+//     finalisation computes the cancellation factor from the same sums and hands the frame to the careful path
+//     (amc_device.cuh) when it exceeds 4 (phases clustered away from 0 and +-pi/2, or a frequency mean above
+//     0.4 sigma - a carrier offset of more than ~0.1 cycles/sample on noisy data): correct, not fast.  Only the
+//     amplitude statistics (FP64, |r - mean r|) still need pass 2.
 #pragma once
 #include "amc_fused.cuh"
 
@@ -137,7 +146,8 @@ __global__ void init_twiddle16dif_kernel() {
 __device__ __forceinline__ int swz16(int e) { return e ^ ((e >> 4) & 15); }
 
 constexpr int kTRow = 17;         // float2 per lane row of the warp-private exchange buffer (16 + 1 pad)
-constexpr int kPend16Stride = 25; // doubles per parked frame (25 totals; odd stride: conflict-free lane-per-frame reads)
+constexpr int kPend16Stride = 29; // doubles per parked frame (28 totals; odd stride: conflict-free lane-per-frame reads)
+constexpr int kPartD16 = 28;
 
 template <int N, typename CT>
 struct Fused16Cfg {
@@ -153,7 +163,7 @@ struct Fused16Cfg {
   static constexpr int T_BYTES = W * 32 * kTRow * 8;                    // warp-private stage-B -> C exchange
   // per (parity, warp): the 25 frame totals as doubles (index = FrameSums order, see park_and_finalize)
   // + the three pass-1 float sums every thread needs right after the barrier (phi, |phi|, f) + pad
-  static constexpr int PART_D = 25, PART_F = 4;
+  static constexpr int PART_D = kPartD16, PART_F = 4;
   static constexpr int PART_BYTES = PART_D * 8 + PART_F * 4;            // 216 per (parity, warp)
   static constexpr int EDGE_BYTES = W * 16 * 4;
   static constexpr int BATCH = 32;                                      // frames finalised together, one lane each
@@ -175,6 +185,33 @@ struct Fused16Cfg {
   static_assert(GROUP_BYTES % 16 == 0, "group region must keep 16-byte alignment");
   static_assert(F * W == 16, "16 sub-transforms per frame");
 };
+
+// Rare: some step of this thread came within kTieEps of +-pi.  Recompute the thread's 16 steps exactly as pass 1 did
+// (same float32 function on the same samples -> the same values), re-decide the near-ties in float64 (np.unwrap's
+// rules) and return the corrections to the four frequency power sums.
+template <int N, typename CT>
+__device__ __noinline__ void tie_corrections16(const CT* xs, int t, float (&corr)[4]) {
+  constexpr int GROUP = N / 16;
+  corr[0] = corr[1] = corr[2] = corr[3] = 0.0f;
+  for (int j = 0; j < 16; ++j) {
+    const int idx = t + GROUP * j;
+    if (idx + 1 >= N) break;
+    double a, b;
+    float af, bf, cf, df;
+    load_sample<CT>(xs + idx, a, b, af, bf);
+    load_sample<CT>(xs + idx + 1, a, b, cf, df);
+    float dd = atan2_fast(df, cf) - atan2_fast(bf, af);
+    if (fabsf(dd) - kPiF > 0.0f) dd -= copysignf(kTwoPiF, dd);
+    if (fabsf(kPiF - fabsf(dd)) < 2.0f * kTieEps) {
+      const float nw = exact_phase_step<CT>(xs, idx);
+      const float o2 = dd * dd, n2 = nw * nw;
+      corr[0] += nw - dd;
+      corr[1] += n2 - o2;
+      corr[2] += n2 * nw - o2 * dd;
+      corr[3] += n2 * n2 - o2 * o2;
+    }
+  }
+}
 
 template <int N, typename CT, int PROF = kProfAll>
 __global__ void __launch_bounds__(Fused16Cfg<N, CT>::CTA, Fused16Cfg<N, CT>::MIN_BLOCKS)
@@ -233,10 +270,12 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
   // Values: 0..14 monomial sums, 15 sum|x|, 16 sum|r-mu|, 17/18 sum (r-mu)^2/^4, 19 sum (phi-mu)^2,
   // 20 sum (|phi|-mu)^2, 21/22 sum (f-mu)^2/^4, 23 sum f, 24 max|X|^2.  Frequency sums were accumulated in
   // radians: 21 <- /(2 pi)^2, 22 <- /(2 pi)^4, 23 <- /(2 pi).
+  // ONE-PASS phase / frequency statistics: parked values 19 sum phi^2, 20 sum t^2 (t = |phi| - pi/2), 21 sum f^2, 22 sum f^4,
+  // 23 sum f, 24 max|X|^2, 25 sum phi, 26 sum t, 27 sum f^3 (f = unwrapped phase step in radians), centred here in float64.
   auto park_and_finalize = [&](int k) {
     const int par = k & 1, bi = k % Cfg::BATCH;
     double* pe = pend + bi * kPend16Stride;
-    if (lane < 25) {
+    if (lane < kPartD16) {
       double s = part_d(par, 0)[lane];
       if (lane == 24) {
 #pragma unroll
@@ -245,8 +284,6 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
 #pragma unroll
         for (int w = 1; w < W; ++w) s += part_d(par, w)[lane];
       }
-      constexpr double k1 = 0.15915494309189533577, k2 = k1 * k1;
-      if (lane >= 21 && lane <= 23) s *= (lane == 21) ? k2 : (lane == 22 ? k2 * k2 : k1);
       pe[lane] = s;
     }
     if (bi == Cfg::BATCH - 1 || k == my_frames - 1) {
@@ -260,17 +297,28 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         fs.c_abs1 = pl[16];
         fs.c2 = pl[17];
         fs.c4 = pl[18];
-        fs.ph_m2 = pl[19];
-        fs.aph_m2 = pl[20];
-        fs.f_m2 = pl[21];
-        fs.f_m4 = pl[22];
-        fs.mean_f = pl[23] / (N - 1);
+        constexpr double dn = N, n1 = N - 1;
+        constexpr double k1 = 0.15915494309189533577, k2 = k1 * k1;
+        const double ph_m2 = pl[19] - pl[25] * pl[25] / dn;
+        const double aph_m2 = pl[20] - pl[26] * pl[26] / dn;
+        const double mu_f = pl[23] / n1;
+        const double f_m2 = pl[21] - pl[23] * mu_f;
+        const double f_m4 = pl[22] - 4.0 * mu_f * pl[27] + 6.0 * mu_f * mu_f * pl[21] - 3.0 * n1 * mu_f * mu_f * mu_f * mu_f;
+        fs.ph_m2 = ph_m2;
+        fs.aph_m2 = aph_m2;
+        fs.f_m2 = f_m2 * k2;
+        fs.f_m4 = f_m4 * k2 * k2;
+        fs.mean_f = mu_f * k1;
         fs.spec_max = pl[24];
+        // cancellation factor of the float32 raw sums <= 4, frequency mean small against its spread; otherwise the
+        // careful path recomputes the frame
+        const bool unsafe = DO_PHASE && (!(pl[19] <= 4.0 * ph_m2) || !(pl[20] <= 4.0 * aph_m2) ||
+                                         !(mu_f * mu_f * n1 <= 0.16 * f_m2));
         const int64_t fo = gg + static_cast<int64_t>(k - bi + lane) * tg;
         double* row = out + fo * out_stride;
         constexpr int kChecks = ((DO_FFT || DO_PHASE) ? kCheckRange : 0) | (DO_PHASE ? kCheckPhase : 0) |
                                 (DO_AMP ? kCheckAmp : 0);
-        if (!finalize_features(fs, N, row, kChecks, ticket)) blank_skipped_groups<PROF>(row);
+        if (!finalize_features(fs, N, row, kChecks | (unsafe ? kCheckForce : 0), ticket)) blank_skipped_groups<PROF>(row);
       }
       __syncwarp();
     }
@@ -289,11 +337,32 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
 
     mbar_wait(bar, static_cast<uint32_t>(par));        // frame `it` has landed in the x slot
 
-    // ---------------------------------------------------------------- pass 1
+    // ---------------------------------------------------------------- pass 1 (the only pass over phase / frequency)
+    // phase of the sample after this warp's run of 32, for every j: lane j evaluates it, lane 31 uses it
+    if constexpr (DO_PHASE) {
+      if (lane < SPT) {
+        const int te = opaque_if<Cfg::REG_BOUND>(t);
+        const int idx = 32 * ((te >> 5) + 1) + GROUP * (te & 31);
+        float pe = 0.0f;
+        if (idx < N) {
+          double a, b;
+          float af, bf;
+          load_sample<CT>(xs + idx, a, b, af, bf);
+          pe = atan2_fast(bf, af);
+        }
+        edge_s[lane] = pe;
+      }
+      __syncwarp();
+    }
     Monomials mono;
     double sum_r;
     double r[SPT];
-    float ph[SPT], xr[SPT], xi[SPT];
+    float xr[SPT], xi[SPT];
+    float s_ph = 0.0f, s_aph = 0.0f, s_p2 = 0.0f, s_t2 = 0.0f;   // s_aph = sum t, t = |phi| - pi/2
+    float s_f = 0.0f, s_f2 = 0.0f, s_f3 = 0.0f, s_f4 = 0.0f;
+    float tie_min = 1.0f;                                      // min | |dd| - pi | over this thread's steps
+    const float last_keep = (t == GROUP - 1) ? 0.0f : 1.0f;   // sample N-1 has no successor
+    float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
       double a, b;
@@ -312,68 +381,39 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         r[j] = 0.0;
         sum_r = 0.0;
       }
-      if constexpr (DO_PHASE) ph[j] = atan2_fast(xi[j], xr[j]);
-      else ph[j] = 0.0f;
-    }
-    float fq[SPT];                                             // unwrapped phase steps in RADIANS (scaled in park)
-    float s_ph = 0.0f, s_aph = 0.0f, s_f = 0.0f;
-    const float last_keep = (t == GROUP - 1) ? 0.0f : 1.0f;   // sample N-1 has no successor
-    if constexpr (!DO_PHASE) {
-#pragma unroll
-      for (int j = 0; j < SPT; ++j) fq[j] = 0.0f;
-    } else {
-    // phase of the sample after this warp's run of 32, for every j: lane j evaluates it, lane 31 uses it
-    if (lane < SPT) {
-      const int te = opaque_if<Cfg::REG_BOUND>(t);
-      const int idx = 32 * ((te >> 5) + 1) + GROUP * (te & 31);
-      float pe = 0.0f;
-      if (idx < N) {
-        double a, b;
-        float af, bf;
-        load_sample<CT>(xs + idx, a, b, af, bf);
-        pe = atan2_fast(bf, af);
-      }
-      edge_s[lane] = pe;
-    }
-    __syncwarp();
-    // wrapped phase differences (np.unwrap); differences within kTieEps of +-pi are only flagged
-    // here and re-decided in FP64 after the loop, so the hot loop stays branch-free
-    float tie_min = 1.0f;                                      // min | |dd| - pi | over this thread's steps
-    float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < SPT; ++j) {
-      float nb = __shfl_down_sync(0xffffffffu, ph[j], 1);
-      if ((j & 3) == 0) e4 = reinterpret_cast<const float4*>(edge_s)[j >> 2];   // uniform address: broadcast
-      const float ej = (j & 3) == 0 ? e4.x : ((j & 3) == 1 ? e4.y : ((j & 3) == 2 ? e4.z : e4.w));
-      if (lane == 31) nb = ej;
-      float dd = nb - ph[j];
-      const float over = fabsf(dd) - kPiF;
-      tie_min = fminf(tie_min, fabsf(over));
-      if (over > 0.0f) dd -= copysignf(kTwoPiF, dd);
-      if (j == SPT - 1) dd *= last_keep;
-      fq[j] = dd;
-      s_ph += ph[j];
-      s_aph += fabsf(ph[j]);
-    }
-    if (tie_min < kTieEps) {   // rare (about once per 10^5 samples on noisy data)
-      // a step whose raw difference was within kTieEps of +-pi ends up within kTieEps of +-pi after the
-      // wrap as well; re-deciding a few extra steps exactly is harmless.  (The step after sample N-1 was
-      // forced to 0 above and is never selected.)
-      unsigned tie_mask = 0u;
-#pragma unroll
-      for (int j = 0; j < SPT; ++j)
-        if (fabsf(kPiF - fabsf(fq[j])) < 2.0f * kTieEps) tie_mask |= 1u << j;
-      while (tie_mask != 0u) {
-        const int j = __ffs(tie_mask) - 1;
-        tie_mask &= tie_mask - 1u;
-        const float val = exact_phase_step<CT>(xs, t + GROUP * j);
-#pragma unroll
-        for (int q = 0; q < SPT; ++q) fq[q] = (q == j) ? val : fq[q];
+      if constexpr (DO_PHASE) {
+        const float ph = atan2_fast(xi[j], xr[j]);
+        float nb = __shfl_down_sync(0xffffffffu, ph, 1);
+        if ((j & 3) == 0) e4 = reinterpret_cast<const float4*>(edge_s)[j >> 2];   // uniform address: broadcast
+        const float ej = (j & 3) == 0 ? e4.x : ((j & 3) == 1 ? e4.y : ((j & 3) == 2 ? e4.z : e4.w));
+        if (lane == 31) nb = ej;
+        float dd = nb - ph;
+        const float over = fabsf(dd) - kPiF;
+        tie_min = fminf(tie_min, fabsf(over));
+        if (over > 0.0f) dd -= copysignf(kTwoPiF, dd);
+        if (j == SPT - 1) dd *= last_keep;
+        s_ph += ph;
+        const float tt = fabsf(ph) - kPiO2F;
+        s_aph += tt;
+        s_p2 = fmaf(ph, ph, s_p2);
+        s_t2 = fmaf(tt, tt, s_t2);
+        const float d2 = dd * dd;
+        s_f += dd;
+        s_f2 += d2;
+        s_f3 = fmaf(d2, dd, s_f3);
+        s_f4 = fmaf(d2, d2, s_f4);
       }
     }
-#pragma unroll
-    for (int j = 0; j < SPT; ++j) s_f += fq[j];
-    }   // DO_PHASE
+    if constexpr (DO_PHASE) {
+      if (tie_min < kTieEps) {   // rare (about once per 10^5 samples on noisy data)
+        float corr[4];
+        tie_corrections16<N, CT>(xs, t, corr);
+        s_f += corr[0];
+        s_f2 += corr[1];
+        s_f3 += corr[2];
+        s_f4 += corr[3];
+      }
+    }
     {
       // 16 FP64 partials per lane -> 16 warp totals: transposed through the warp-private buffer
       // (16 STS.64 + 16 LDS.64 + 16 DADD; the shuffle butterfly needed 60 selects + 32 shuffles).
@@ -384,8 +424,8 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
 #pragma unroll
       for (int i = 0; i < 15; ++i) red[lane * kTRow + i] = mono.s[i];
       red[lane * kTRow + 15] = sum_r;
-      float accf[4] = {s_ph, s_aph, s_f, 0.0f};
-      warp_sum_multi<float, 4>(accf, lane);
+      float accf[8] = {s_p2, s_t2, s_f2, s_f4, s_f, s_ph, s_aph, s_f3};   // -> parked 19, 20, 21, 22, 23, 25, 26, 27
+      warp_sum_multi<float, 8>(accf, lane);
       __syncwarp();
       const double* col = red + (lane >> 4) * (16 * kTRow) + (lane & 15);
       double cs[16];
@@ -400,8 +440,10 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       // that are about to be overwritten; in steady state this completed long ago
       mbar_wait(rbar, static_cast<uint32_t>(par));
       if (lane < 16) part_d(par, wg)[lane] = tot;
-      if ((lane & 7) == 0 && lane < 24) part_f(par, wg)[lane >> 3] = accf[0];
-      if (lane == 16) part_d(par, wg)[23] = static_cast<double>(accf[0]);   // sum f, again, for the finalisation
+      if ((lane & 3) == 0) {
+        const int kk = lane >> 2;                        // 0..7
+        part_d(par, wg)[19 + kk + (kk >= 5 ? 1 : 0)] = static_cast<double>(accf[0]);
+      }
     }
 
     // ---------------------------------------------------------------- FFT stage A: radix 16 over this
@@ -422,13 +464,6 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       for (int q = 0; q < 16; ++q) v[q] = make_float2(xr[q], xi[q]);
 #endif
       dft16(v);
-#ifdef AMC_TW_V2
-      float2 tw[15];
-#pragma unroll
-      for (int q = 1; q < 16; ++q) tw[q - 1] = g_tw_a[tw_a_offset(N) + (q - 1) * GROUP + tv];   // 256 B per warp load
-#pragma unroll
-      for (int q = 1; q < 16; ++q) v[bitrev4(q)] = c_mul(v[bitrev4(q)], tw[q - 1]);
-#else
       float4 tw[8];
 #pragma unroll
       for (int p = 0; p < 8; ++p) tw[p] = g_tw_a4[tw_a4_offset(N) + p * GROUP + tv];            // 512 B per warp load
@@ -437,7 +472,6 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         const float4 w = tw[(q - 1) >> 1];
         v[bitrev4(q)] = c_mul(v[bitrev4(q)], (q & 1) ? make_float2(w.x, w.y) : make_float2(w.z, w.w));
       }
-#endif
 #pragma unroll
       for (int q = 0; q < 16; ++q) {   // element (t, q) -> row t, slot q ^ rot_t
         const float2 o = v[bitrev4(q)];
@@ -456,17 +490,9 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     if (wg == 0 && it > 0) park_and_finalize(it - 1);   // the previous frame's totals are complete now
 
     double tot_r = 0.0;
-    float tot_ph = 0.0f, tot_aph = 0.0f, tot_f = 0.0f;
 #pragma unroll
-    for (int w = 0; w < W; ++w) {
-      tot_r += part_d(par, w)[15];
-      tot_ph += part_f(par, w)[0];
-      tot_aph += part_f(par, w)[1];
-      tot_f += part_f(par, w)[2];
-    }
+    for (int w = 0; w < W; ++w) tot_r += part_d(par, w)[15];
     const double mu_r = tot_r * (1.0 / N);
-    const float mu_ph = tot_ph * (1.0f / N), mu_aph = tot_aph * (1.0f / N);
-    const float mu_f = tot_f * (1.0f / (N - 1));       // radians
 
     // ---------------------------------------------------------------- pass 2 (registers only)
     {
@@ -474,7 +500,6 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       //  2 % faster, but it exposes the ~5e-14 one-sided bias of sqrt_nr multiplied by (mu/sigma)^2 - 1.3e-9
       //  on the amplitude kurtosis at 30 dB SNR; test_high_snr_amplitude_features_keep_the_1e9_class)
       double c2acc[4] = {0.0, 0.0, 0.0, 0.0};            // sum |r-mu|, sum (r-mu)^2, sum (r-mu)^4, -
-      float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int j = 0; j < SPT; ++j) {
         if constexpr (DO_AMP) {
@@ -484,24 +509,9 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
           c2acc[1] += d2;
           c2acc[2] = fma(d2, d2, c2acc[2]);
         }
-        if constexpr (DO_PHASE) {
-          const float e = ph[j] - mu_ph;
-          q2acc[0] = fmaf(e, e, q2acc[0]);
-          const float ea = fabsf(ph[j]) - mu_aph;
-          q2acc[1] = fmaf(ea, ea, q2acc[1]);
-          float ef = fq[j] - mu_f;
-          if (j == SPT - 1) ef *= last_keep;
-          const float ef2 = ef * ef;
-          q2acc[2] += ef2;
-          q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
-        }
       }
       if constexpr (DO_AMP) warp_sum_multi<double, 4>(c2acc, lane);
-      if constexpr (DO_PHASE) warp_sum_multi<float, 4>(q2acc, lane);
-      if ((lane & 7) == 0) {
-        if (lane < 24) part_d(par, wg)[16 + (lane >> 3)] = c2acc[0];
-        part_d(par, wg)[19 + (lane >> 3)] = static_cast<double>(q2acc[0]);
-      }
+      if ((lane & 7) == 0 && lane < 24) part_d(par, wg)[16 + (lane >> 3)] = c2acc[0];
     }
 
     float vmax = 0.0f;
@@ -518,31 +528,20 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       const int k1b = wv * Cfg::F + (lv >> LOG_M1);                  // sub-transform of this lane in stage B
       const int kk_b = k1b ^ ((m1 << (4 - LOG_M1)) & 15);
       float2* wr_t = tb + lv * kTRow;
-#ifdef AMC_TW_V2
-      float2 tw[15];
-#pragma unroll
-      for (int q = 1; q < 16; ++q) tw[q - 1] = g_tw_b[tw_b_offset(N) + (q - 1) * M1 + m1];
-#else
       float4 tw[8];
 #pragma unroll
       for (int p = 0; p < 8; ++p) tw[p] = g_tw_b4[tw_b4_offset(N) + p * M1 + m1];
-#endif
 #pragma unroll
       for (int m2 = 0; m2 < 16; ++m2) {
         // (n1 & 15) = m1 + M1 (m2 mod 16/M1): the rotated swizzle is base ^ (m2 mod 16/M1)
         v[m2] = buf_a[m1 * 16 + (kk_b ^ (m2 & (16 / M1 - 1))) + 16 * M1 * m2];
       }
       dft16(v);
-#ifdef AMC_TW_V2
-#pragma unroll
-      for (int q = 1; q < 16; ++q) v[bitrev4(q)] = c_mul(v[bitrev4(q)], tw[q - 1]);
-#else
 #pragma unroll
       for (int q = 1; q < 16; ++q) {
         const float4 w = tw[(q - 1) >> 1];
         v[bitrev4(q)] = c_mul(v[bitrev4(q)], (q & 1) ? make_float2(w.x, w.y) : make_float2(w.z, w.w));
       }
-#endif
 #pragma unroll
       for (int q = 0; q < 16; ++q) wr_t[q] = v[bitrev4(q)];
     }

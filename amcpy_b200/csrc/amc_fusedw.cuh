@@ -11,7 +11,7 @@
 namespace amc {
 
 constexpr int kWBatch = 8;
-constexpr int kWPendStride = 25;   // doubles per parked frame (odd: conflict-free lane-per-frame reads)
+constexpr int kWPendStride = 29;   // 28 parked values per frame (odd stride: conflict-free lane-per-frame reads)
 constexpr int kWRow = 17;          // doubles per lane row of the reduction buffer (16 + 1 pad)
 
 template <int N, typename CT>
@@ -108,8 +108,11 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
       if constexpr (DO_PHASE) ph[j] = atan2_fast(xi[j], xr[j]);
       else ph[j] = 0.0f;
     }
-    float fq[SPT];                                            // unwrapped phase steps in RADIANS (scaled when parked)
-    float s_ph = 0.0f, s_aph = 0.0f, s_f = 0.0f;
+    // ONE-PASS phase / frequency statistics (round 2, as in amc_fused16.cuh): raw float32 power sums of phi, of
+    // t = |phi| - pi/2 and of the unwrapped phase steps f (radians), centred in float64 at finalisation
+    float fq[SPT];
+    float s_ph = 0.0f, s_aph = 0.0f, s_p2 = 0.0f, s_t2 = 0.0f;   // s_aph = sum t
+    float s_f = 0.0f, s_f2 = 0.0f, s_f3 = 0.0f, s_f4 = 0.0f;
     const float last_keep = (lane == 31) ? 0.0f : 1.0f;       // sample N-1 has no successor
     if constexpr (!DO_PHASE) {
 #pragma unroll
@@ -128,7 +131,10 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
       if (j == SPT - 1) dd *= last_keep;
       fq[j] = dd;
       s_ph += ph[j];
-      s_aph += fabsf(ph[j]);
+      const float tt = fabsf(ph[j]) - kPiO2F;
+      s_aph += tt;
+      s_p2 = fmaf(ph[j], ph[j], s_p2);
+      s_t2 = fmaf(tt, tt, s_t2);
     }
     if (tie_min < kTieEps) {   // rare (about once per 10^5 samples on noisy data): FP64 re-decision, see amc_fused16.cuh
       unsigned tie_mask = 0u;
@@ -144,7 +150,13 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
       }
     }
 #pragma unroll
-    for (int j = 0; j < SPT; ++j) s_f += fq[j];
+    for (int j = 0; j < SPT; ++j) {
+      const float f2 = fq[j] * fq[j];
+      s_f += fq[j];
+      s_f2 += f2;
+      s_f3 = fmaf(f2, fq[j], s_f3);
+      s_f4 = fmaf(f2, f2, s_f4);
+    }
     }   // DO_PHASE
 
     // 16 FP64 partials per lane -> lane l (and l + 16) holds the warp total of value l
@@ -153,8 +165,8 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
 #pragma unroll
     for (int i = 0; i < 15; ++i) red[lv * kWRow + i] = mono.s[i];
     red[lv * kWRow + 15] = sum_r;
-    float accf[4] = {s_ph, s_aph, s_f, 0.0f};
-    warp_sum_multi<float, 4>(accf, lane);                     // lane l: total of value l >> 3
+    float accf[8] = {s_p2, s_t2, s_f2, s_f4, s_f, s_ph, s_aph, s_f3};   // -> parked 19, 20, 21, 22, 23, 25, 26, 27
+    warp_sum_multi<float, 8>(accf, lane);                     // lane l: total of value l >> 2
     __syncwarp();
     double tot16;
     {
@@ -169,37 +181,20 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
       tot16 = cs[0] + __shfl_xor_sync(FULL, cs[0], 16);
     }
     const double mu_r = __shfl_sync(FULL, tot16, 15) * (1.0 / N);
-    const float mu_ph = __shfl_sync(FULL, accf[0], 0) * (1.0f / N);
-    const float mu_aph = __shfl_sync(FULL, accf[0], 8) * (1.0f / N);
-    const float tot_f = __shfl_sync(FULL, accf[0], 16);
-    const float mu_f = tot_f * (1.0f / (N - 1));              // radians
 
     // ---------------------------------------------------------------- pass 2 (registers only)
     double c2acc[4] = {0.0, 0.0, 0.0, 0.0};                   // sum |r-mu|, sum (r-mu)^2, sum (r-mu)^4, -
-    float q2acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if constexpr (DO_AMP) {
 #pragma unroll
-    for (int j = 0; j < SPT; ++j) {
-      if constexpr (DO_AMP) {
+      for (int j = 0; j < SPT; ++j) {
         const double d = r[j] - mu_r;
         const double d2 = d * d;
         c2acc[0] += fabs(d);
         c2acc[1] += d2;
         c2acc[2] = fma(d2, d2, c2acc[2]);
       }
-      if constexpr (DO_PHASE) {
-        const float e = ph[j] - mu_ph;
-        q2acc[0] = fmaf(e, e, q2acc[0]);
-        const float ea = fabsf(ph[j]) - mu_aph;
-        q2acc[1] = fmaf(ea, ea, q2acc[1]);
-        float ef = fq[j] - mu_f;
-        if (j == SPT - 1) ef *= last_keep;
-        const float ef2 = ef * ef;
-        q2acc[2] += ef2;
-        q2acc[3] = fmaf(ef2, ef2, q2acc[3]);
-      }
+      warp_sum_multi<double, 4>(c2acc, lane);                 // lane l: value l >> 3
     }
-    if constexpr (DO_AMP) warp_sum_multi<double, 4>(c2acc, lane);   // lane l: value l >> 3
-    if constexpr (DO_PHASE) warp_sum_multi<float, 4>(q2acc, lane);
 
     // ---------------------------------------------------------------- FFT 8 x 8 x 4 through the slot
     __syncwarp();                                             // every lane has finished reading x
@@ -250,17 +245,17 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
                     &bars[slot], l2_evict_first_policy());
     }
 
-    // ---------------------------------------------------------------- park this frame's 25 totals
+    // ---------------------------------------------------------------- park this frame's 28 totals: 0..14 monomial
+    // sums, 15 sum|x|, 16..18 centred amplitude sums, 19 sum phi^2, 20 sum t^2, 21 sum f^2, 22 sum f^4, 23 sum f, 24 max,
+    // 25 sum phi, 26 sum t, 27 sum f^3
     const int bi = it % kWBatch;
     double* pe = pend + bi * kWPendStride;
-    constexpr double kInv2Pi = 0.15915494309189533577, kInv2Pi2 = kInv2Pi * kInv2Pi;
     if (lane < 16) pe[lane] = tot16;                                   // 0..15
-    if ((lane & 7) == 0) {                                             // 16..18, 19..22; frequency sums: radians -> cycles
-      if (lane < 24) pe[16 + (lane >> 3)] = c2acc[0];
-      const double sc = (lane == 16) ? kInv2Pi2 : (lane == 24 ? kInv2Pi2 * kInv2Pi2 : 1.0);
-      pe[19 + (lane >> 3)] = static_cast<double>(q2acc[0]) * sc;
+    if ((lane & 7) == 0 && lane < 24) pe[16 + (lane >> 3)] = c2acc[0];
+    if ((lane & 3) == 0) {
+      const int kk = lane >> 2;                                        // 0..7
+      pe[19 + kk + (kk >= 5 ? 1 : 0)] = static_cast<double>(accf[0]);
     }
-    if (lane == 1) pe[23] = static_cast<double>(tot_f) * kInv2Pi;
     if (lane == 3) pe[24] = static_cast<double>(vmax);
     if (bi == kWBatch - 1 || it == my_frames - 1) {
       __syncwarp();
@@ -273,16 +268,28 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
         fs.c_abs1 = pl[16];
         fs.c2 = pl[17];
         fs.c4 = pl[18];
-        fs.ph_m2 = pl[19];
-        fs.aph_m2 = pl[20];
-        fs.f_m2 = pl[21];
-        fs.f_m4 = pl[22];
-        fs.mean_f = pl[23] / (N - 1);
+        constexpr double dn = N, n1 = N - 1;
+        constexpr double k1 = 0.15915494309189533577, k2 = k1 * k1;
+        const double ph_m2 = pl[19] - pl[25] * pl[25] / dn;
+        const double aph_m2 = pl[20] - pl[26] * pl[26] / dn;
+        const double mu_f = pl[23] / n1;
+        const double f_m2 = pl[21] - pl[23] * mu_f;
+        const double f_m4 = pl[22] - 4.0 * mu_f * pl[27] + 6.0 * mu_f * mu_f * pl[21] - 3.0 * n1 * mu_f * mu_f * mu_f * mu_f;
+        fs.ph_m2 = ph_m2;
+        fs.aph_m2 = aph_m2;
+        fs.f_m2 = f_m2 * k2;                                           // radians -> cycles
+        fs.f_m4 = f_m4 * k2 * k2;
+        fs.mean_f = mu_f * k1;
         fs.spec_max = pl[24];
+        // cancellation factor of the float32 raw sums <= 4, frequency mean small against its spread; otherwise the
+        // careful path recomputes the frame
+        const bool unsafe = DO_PHASE && (!(pl[19] <= 4.0 * ph_m2) || !(pl[20] <= 4.0 * aph_m2) ||
+                                         !(mu_f * mu_f * n1 <= 0.16 * f_m2));
         const int64_t fo = gg + static_cast<int64_t>(it - bi + lane) * tg;
         constexpr int kChecks = ((DO_FFT || DO_PHASE) ? kCheckRange : 0) | (DO_PHASE ? kCheckPhase : 0) |
                                 (DO_AMP ? kCheckAmp : 0);
-        if (!finalize_features(fs, N, out + fo * out_stride, kChecks, ticket)) blank_skipped_groups<PROF>(out + fo * out_stride);
+        if (!finalize_features(fs, N, out + fo * out_stride, kChecks | (unsafe ? kCheckForce : 0), ticket))
+          blank_skipped_groups<PROF>(out + fo * out_stride);
       }
       __syncwarp();
     }
