@@ -238,7 +238,7 @@ __device__ __forceinline__ Cplx cscale(Cplx a, double k) { return {a.re * k, a.i
 __device__ __forceinline__ Cplx cadd(Cplx a, Cplx b) { return {a.re + b.re, a.im + b.im}; }
 __device__ __forceinline__ Cplx csub(Cplx a, Cplx b) { return {a.re - b.re, a.im - b.im}; }
 __device__ __forceinline__ Cplx cconj(Cplx a) { return {a.re, -a.im}; }
-__device__ __forceinline__ double cabs(Cplx a) { return hypot(a.re, a.im); }
+__device__ __forceinline__ double cabs(Cplx a) { return hypot(a.re, a.im); }   // np.abs (sqrt(re^2+im^2): -0.2 %, not taken)
 
 // Feature groups one instantiation of a fused kernel computes (amc_fused16.cuh, amc_fusedw.cuh).  The C ABI's feature_mask picks the cheapest compiled
 // profile that covers the requested features (amc_api.cu: pick_profile); columns of groups that were not

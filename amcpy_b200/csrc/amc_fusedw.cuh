@@ -161,7 +161,7 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
 
     // 16 FP64 partials per lane -> lane l (and l + 16) holds the warp total of value l
     __syncwarp();                                             // the previous frame's column reads are done
-    const int lv = opaque_if<true>(lane);
+        const int lv = opaque_if<true>(lane);               // (without it: 32 B of spills at the 128-register cap, -2.5 %)
 #pragma unroll
     for (int i = 0; i < 15; ++i) red[lv * kWRow + i] = mono.s[i];
     red[lv * kWRow + 15] = sum_r;
