@@ -8,3 +8,7 @@ python tools/profile_families.py > gpurun_out/r2_families_plain.jsonl 2> gpurun_
 ncu --set full --clock-control none --profile-from-start off -f -o /tmp/r2_families \
     python tools/profile_families.py > gpurun_out/r2_ncu3.log 2>&1
 python tools/ncu_summary.py /tmp/r2_families.ncu-rep > gpurun_out/r2_families_summary.txt 2>&1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/r2p_pytest.log
+python bench.py > gpurun_out/r2p_bench.json 2> gpurun_out/r2p_bench.err
+python tools/sweep.py --steps 30 > gpurun_out/r2p_sweep.jsonl 2>&1
+python tools/sweep.py --steps 30 --dtype c64 > gpurun_out/r2p_sweep_c64.jsonl 2>&1
