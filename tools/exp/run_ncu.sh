@@ -1,8 +1,3 @@
-# ncu evidence of the round (one gpurun call; each command has exited 0 without ncu first - gpurun checks that itself):
-#  1. launch list of the benchmark command (shares of the step, cold-cache serialised times)
-#  2. --set full capture of the hot kernel (source page: compiled with -lineinfo); the report comes back (~17 MB)
-#  3. --set full capture of one launch of every shipped kernel family (tools/profile_families.py); the report stays on
-#     the box (hundreds of MB), only its summaries come back
 set -x
 python bench.py --no-e2e --steps 20 --warmup 3 > gpurun_out/r2_plain.json 2> gpurun_out/r2_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r2_launches.csv \
@@ -13,7 +8,7 @@ python tools/profile_families.py > gpurun_out/r2_families_plain.jsonl 2> gpurun_
 ncu --set full --clock-control none --profile-from-start off -f -o /tmp/r2_families \
     python tools/profile_families.py > gpurun_out/r2_ncu3.log 2>&1
 python tools/ncu_summary.py /tmp/r2_families.ncu-rep > gpurun_out/r2_families_summary.txt 2>&1
-ls -la /tmp/r2_families.ncu-rep gpurun_out >> gpurun_out/r2_ncu3.log
-python bench.py > gpurun_out/r2e_bench.json 2> gpurun_out/r2e_bench.err
-python tools/sweep.py --steps 30 > gpurun_out/r2e_sweep.jsonl 2>&1
-du -sh gpurun_out >> gpurun_out/r2_ncu3.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/r2p_pytest.log
+python bench.py > gpurun_out/r2p_bench.json 2> gpurun_out/r2p_bench.err
+python tools/sweep.py --steps 30 > gpurun_out/r2p_sweep.jsonl 2>&1
+python tools/sweep.py --steps 30 --dtype c64 > gpurun_out/r2p_sweep_c64.jsonl 2>&1
