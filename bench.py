@@ -621,18 +621,28 @@ def run_cuda_arm(args):
     if affinity0 is not None and numa_cpus:
         os.sched_setaffinity(0, affinity0)   # the CPU baselines below use every core of the box again
 
-    strong = None if args.quick else strong_scaling_config3(rank, world, dev, dist)
-    gather = gather_timing(rank, world, dev, dist, x, n_frames) if (world > 1 and not args.quick) else None
+    def guarded(name, fn):
+        """An auxiliary leg must never cost the headline line: its failure is reported under its own key.  (Collective
+        legs run on every rank, so a failure inside one of them is the same exception on every rank.)"""
+        try:
+            return fn()
+        except Exception as e:  # noqa: BLE001
+            print(f"bench.py: leg '{name}' failed: {type(e).__name__}: {e}", file=sys.stderr)
+            return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+    strong = None if args.quick else guarded("strong_scaling", lambda: strong_scaling_config3(rank, world, dev, dist))
+    gather = guarded("gather", lambda: gather_timing(rank, world, dev, dist, x, n_frames)) if (world > 1 and not args.quick) else None
     del xh, oh, x
     torch.cuda.empty_cache()
-    stage = stage_timing(dev) if (world == 1 and rank == 0 and not args.quick) else None
+    stage = guarded("stage", lambda: stage_timing(dev)) if (world == 1 and rank == 0 and not args.quick) else None
 
     if rank == 0:
         peak, peak_src = _peaks()
         achieved = n_frames * BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
         traffic, traffic_src = _measured_traffic()
-        cpu = run_cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
-        shipped = run_cpu_baseline_as_shipped() if (world == 1 and not args.no_cpu_baseline and not args.quick) else None
+        cpu = guarded("cpu_baseline", run_cpu_baseline) if (world == 1 and not args.no_cpu_baseline) else None
+        shipped = (guarded("cpu_baseline_as_shipped", run_cpu_baseline_as_shipped)
+                   if (world == 1 and not args.no_cpu_baseline and not args.quick) else None)
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
