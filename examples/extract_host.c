@@ -32,10 +32,17 @@ int main(int argc, char** argv) {
     return 1;
   }
   printf("argument check: %s\n", amc_last_error_string());
+  /* what the library itself would allocate for this call shape (device path at a power-of-two size: nothing) */
+  printf("workspace: device path %lld B, host path %lld B\n", (long long)amc_workspace_bytes(AMC_C128, n_frames, n, 0),
+         (long long)amc_workspace_bytes(AMC_C128, n_frames, n, 1));
   const int devices = amc_device_count();
   if (devices < 1) {
     printf("no CUDA device (%d): %s - nothing computed, there is no CPU path\n", devices, amc_last_error_string());
     return 0;
+  }
+  if (amc_init(0) != AMC_OK) { /* optional: builds the tables now instead of on the first call */
+    fprintf(stderr, "amc_init failed: %s\n", amc_last_error_string());
+    return 1;
   }
   double* iq = (double*)malloc((size_t)n_frames * n * 2 * sizeof(double));
   double* out = (double*)malloc((size_t)n_frames * AMC_N_FEATURES * sizeof(double));
