@@ -66,6 +66,7 @@ struct DeviceState {
   bool tw_done = false;
   cudaStream_t init_stream = nullptr;
   cudaEvent_t tw_event = nullptr;
+  cudaMemPool_t ws_pool = nullptr;   // the library's own stream-ordered pool (scratch of the long-frame / general kernels)
 };
 DeviceState g_dev[kMaxDevices];
 
@@ -95,6 +96,29 @@ int device_info(DevInfo* di) {
   }
   di->dev = dev;
   di->sms = g_dev[dev].sms;
+  return AMC_OK;
+}
+
+// Stream-ordered scratch from the library's OWN memory pool (never the process-wide default pool, whose release
+// threshold belongs to the application): memory is kept across calls, so a steady stream of launches allocates once.
+int ws_alloc(int dev, void** ptr, size_t bytes, cudaStream_t stream) {
+  cudaMemPool_t pool;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceState& d = g_dev[dev];
+    if (!d.ws_pool) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      AMC_CUDA(cudaMemPoolCreate(&d.ws_pool, &props));
+      unsigned long long keep = ~0ull;
+      AMC_CUDA(cudaMemPoolSetAttribute(d.ws_pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    pool = d.ws_pool;
+  }
+  AMC_CUDA(cudaMallocFromPoolAsync(ptr, bytes, pool, stream));
   return AMC_OK;
 }
 
@@ -480,7 +504,7 @@ int launch_large(const void* iq, int64_t n_frames, int64_t frame_stride, double*
   const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
   // |x| scratch: N doubles per CTA from the stream-ordered pool (no synchronisation); without it the kernel recomputes
   double* ws = nullptr;
-  if (cudaMallocAsync(reinterpret_cast<void**>(&ws), static_cast<size_t>(grid) * N * sizeof(double), stream) != cudaSuccess) {
+  if (ws_alloc(dev, reinterpret_cast<void**>(&ws), static_cast<size_t>(grid) * N * sizeof(double), stream) != AMC_OK) {
     cudaGetLastError();
     ws = nullptr;
   }
@@ -657,12 +681,15 @@ int launch_general(const void* iq, int64_t n_frames, int64_t n, int64_t frame_st
   int64_t cap = static_cast<int64_t>(sms) * 4;
   float2* ws = nullptr;
   if (ws_elems > 0) {
-    // stream-ordered workspace (cudaMallocAsync / cudaFreeAsync on the caller's stream: no synchronisation, safe
+    // stream-ordered workspace (the library's own memory pool, allocation and free on the caller's stream: no synchronisation, safe
     // between concurrent calls); the grid is trimmed so that it stays below kFftWorkspaceMax
     const int64_t fit = static_cast<int64_t>(kFftWorkspaceMax / (ws_elems * sizeof(float2)));
     if (cap > fit) cap = fit < 1 ? 1 : fit;
     const int64_t ctas = n_frames < cap ? n_frames : cap;
-    AMC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), static_cast<size_t>(ctas) * ws_elems * sizeof(float2), stream));
+    int dev_ws = 0;
+    AMC_CUDA(cudaGetDevice(&dev_ws));
+    rc = ws_alloc(dev_ws, reinterpret_cast<void**>(&ws), static_cast<size_t>(ctas) * ws_elems * sizeof(float2), stream);
+    if (rc != AMC_OK) return rc;
   }
   const int grid = static_cast<int>(n_frames < cap ? n_frames : cap);
   amc::general_features_kernel<CT><<<grid, amc::kGenThreads, dyn, stream>>>(
