@@ -985,6 +985,15 @@ int64_t amc_workspace_bytes(int iq_dtype, int64_t n_frames, int64_t frame_size, 
     if (ctas < 1) ctas = 1;
     bytes += (n_frames < ctas ? n_frames : ctas) * per;
   }
+  if (frame_size == 8192 || frame_size == 16384) {  // |x| scratch of the long-frame kernel: N doubles per resident CTA
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      cudaGetLastError();
+      sms = 148;                                    // no device visible: a B200's SM count
+    }
+    const int64_t ctas = static_cast<int64_t>(sms) * (frame_size == 8192 ? 2 : 1);
+    bytes += (n_frames < ctas ? n_frames : ctas) * frame_size * static_cast<int64_t>(sizeof(double));
+  }
   if (host_path) {                                  // double-buffered chunk buffers of one pipe
     const int64_t elt = iq_dtype == AMC_C128 ? 16 : 8;
     const int64_t frame_bytes = frame_size * elt;

@@ -95,10 +95,12 @@ int amc_version(void);
 int amc_init(int device);
 
 /*
- * Device memory (bytes) the library itself allocates - once, cached - for calls of this shape: Bluestein tables of a
- * non-power-of-two frame_size (amc_extract_batch) and, when host_path != 0, the double-buffered chunk buffers of
- * amc_extract_host / amc_extract_host_planar.  0 for the device-pointer path at power-of-two sizes: the caller owns
- * every buffer there.  Negative = AMC_ERR_*.
+ * Device memory (bytes) the library itself allocates - once, cached or kept in its own stream-ordered memory pool - for
+ * calls of this shape: Bluestein tables of a non-power-of-two frame_size, the FFT workspace of frames longer than
+ * 16384 samples, the |x| scratch of the long-frame kernel (frame_size 8192 / 16384: N doubles per resident CTA) and,
+ * when host_path != 0, the double-buffered chunk buffers of amc_extract_host / amc_extract_host_planar.  0 for the
+ * device-pointer path at frame sizes 256..4096 (and any other power of two <= 4096): the caller owns every buffer
+ * there.  Negative = AMC_ERR_*.
  */
 int64_t amc_workspace_bytes(int iq_dtype, int64_t n_frames, int64_t frame_size, int host_path);
 
