@@ -22,3 +22,20 @@ for ids in ([10, 18], [6, 12], [2, 4, 6, 8, 12, 14]):
         a = ops.extract_features(x, feature_mask=ops.feature_mask_of(ids))
         torch.cuda.synchronize()
         print(ids, n, bool(torch.isfinite(a[:, [i - 1 for i in ids]]).all()))
+# round 2: the careful path (tagged rows recomputed by the general kernel in redo mode), long frames through the global FFT
+# workspace, Bluestein beyond the shared-memory limit, the host pipeline (pipe pool) and the re-layout kernels
+import numpy as np  # noqa: E402
+
+for n in (256, 2048, 8192):
+    x = torch.randn((64, n), dtype=torch.complex128, device="cuda", generator=g)
+    x[::4] = 1.0 + 1e-3 * x[::4]                 # narrow phase clusters -> careful path
+    x[1::8] *= 1e-30                             # out of the float32 range -> careful path
+    a = ops.extract_features(x)
+    torch.cuda.synchronize()
+    print("careful", n, bool(torch.isfinite(a).all()))
+for n, frames in ((32768, 6), (12000, 6)):
+    x = torch.randn((frames, n), dtype=torch.complex128, device="cuda", generator=g)
+    print("long", n, bool(torch.isfinite(ops.extract_features(x)).all()))
+xh = (np.random.default_rng(0).standard_normal((300, 2048)) + 1j * np.random.default_rng(1).standard_normal((300, 2048)))
+print("host", bool(np.isfinite(ops.extract_features_host(xh)).all()),
+      bool(np.isfinite(ops.extract_features_host(np.asfortranarray(xh))).all()))
