@@ -482,3 +482,31 @@ def test_concurrent_host_calls_share_a_device(torch_cuda):
         got = list(pool.map(ops.extract_features_host, rng_sets))
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
+
+
+def test_concurrent_streams_with_careful_path_frames(torch_cuda):
+    """Eight streams enqueue extractions at once, every batch holding frames the careful path has to redo: the per-launch
+    ticket ring must neither lose a tagged row nor touch another launch's output (slots only grow: atomicMax)."""
+    from amcpy_b200 import ops, synth
+    from conftest import golden_narrow
+
+    xn, _ = golden_narrow(2048)
+    batches = []
+    for k in range(8):
+        base = np.concatenate([synth.cell(m, 8.0, 9, range(20), 2048, seed=70 + k) for m in range(6)])
+        base[k::11] = xn[k % 10]                               # sprinkle narrow / extreme-scale frames
+        batches.append(torch_cuda.from_numpy(base).cuda())
+    want = [ops.extract_features(b).clone() for b in batches]
+    torch_cuda.cuda.synchronize()
+    streams = [torch_cuda.cuda.Stream() for _ in batches]
+    outs = [torch_cuda.empty_like(w) for w in want]
+    for rep in range(5):
+        for o in outs:
+            o.zero_()
+        torch_cuda.cuda.synchronize()
+        for b, o, s in zip(batches, outs, streams):
+            ops.extract_features(b, out=o, stream=s)
+        torch_cuda.cuda.synchronize()
+        for o, w in zip(outs, want):
+            assert torch_cuda.equal(o, w)
+            assert not (o[:, 0].view(torch_cuda.int64) == 0x7ff8b200a3c10001).any()   # no tag left behind
