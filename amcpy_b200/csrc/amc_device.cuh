@@ -150,15 +150,30 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
   p = fmaf(p, s, -0.14185972498001842f);
   p = fmaf(p, s, 0.19990396259243107f);
   p = fmaf(p, s, -0.33332987041851964f);
-  float r = fmaf(q * s, p, q);                              // [0, pi/4]
-  const float swap = (ay > ax) ? 1.0f : 0.0f;               // FSET.BF
-  r = fabsf(fmaf(swap, -kPiO2F, r));                        // ay > ax: pi/2 - r
-  const int neg = __float_as_int(x) >> 31;                  // all ones when the sign bit of x is set
-  r = fabsf(r - __int_as_float(neg & __float_as_int(kPiF)));  // x < 0 (or -0): pi - r
+  const float r0 = fmaf(q * s, p, q);                       // atan(q) in [0, pi/4]
+  // Octant and quadrant in five instructions: with r1 = (ay > ax ? pi/2 - r0 : r0) the answer is
+  // copysign(x >= 0 ? r1 : pi - r1, y) = copysign(pi/2 - copysign(pi/2 - r1, x), y), and
+  // u = pi/2 - r1 = | r0 - [ay <= ax] pi/2 | needs no separate r1 (round 1 spent six: the sign of x through an integer
+  // shift + mask; 0.6023 -> 0.5951 ms at N = 2048).  Signs travel as bits, so x = -0 counts as negative like np.angle / atan2 do; pi/2 + pi/2 is exactly
+  // the float32 pi that pi - r1 used.
+  const float keep = (ay > ax) ? 0.0f : 1.0f;               // FSET.BF
+  const float u = fmaf(keep, -kPiO2F, r0);                  // +-(pi/2 - r1); only the magnitude is used
+  unsigned vb;                                              // copysign(|u|, x) as ONE LOP3: (u & ~m) | (x & m)  (LUT 0xD8)
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=r"(vb) : "r"(__float_as_uint(u)), "r"(__float_as_uint(x)));
+  const float r = kPiO2F - __uint_as_float(vb);             // [0, pi]
   // copysign(r, y) as ONE LOP3: (r & ~m) | (y & m), m = sign mask  (LUT 0xD8)
   unsigned res;
   asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=r"(res) : "r"(__float_as_uint(r)), "r"(__float_as_uint(y)));
   return __uint_as_float(res);
+}
+
+// One float32 step of np.unwrap away from the ties: dd - 2 pi rint(dd / 2 pi), |dd| < 2 pi + eps, with the rounding done by
+// the 1.5 * 2^23 trick - three FP32-pipe instructions and no predicate (compare + copysign + predicated add: four).  For
+// k = +-1 the fused multiply-add returns the same float as dd -+ kTwoPiF.  The decision boundary sits within 2e-7 of pi;
+// callers treat every step that ends within kTieEps of +-pi as a tie and re-decide it in float64.
+__device__ __forceinline__ float wrap_step_f32(float dd) {
+  const float k = __fadd_rn(fmaf(dd, kInvTwoPiF, 12582912.0f), -12582912.0f);
+  return fmaf(k, -kTwoPiF, dd);
 }
 
 // ------------------------------------------------------------------ |x| in float64 without DSQRT

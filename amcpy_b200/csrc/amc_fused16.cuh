@@ -204,8 +204,7 @@ __device__ __noinline__ void tie_corrections16(const CT* xs, int t, float (&corr
     float af, bf, cf, df;
     load_sample<CT>(xs + idx, a, b, af, bf);
     load_sample<CT>(xs + idx + 1, a, b, cf, df);
-    float dd = atan2_fast(df, cf) - atan2_fast(bf, af);
-    if (fabsf(dd) - kPiF > 0.0f) dd -= copysignf(kTwoPiF, dd);
+    const float dd = wrap_step_f32(atan2_fast(df, cf) - atan2_fast(bf, af));
     if (fabsf(kPiF - fabsf(dd)) < 2.0f * kTieEps) {
       const float nw = exact_phase_step<CT>(xs, idx);
       const float o2 = dd * dd, n2 = nw * nw;
@@ -364,7 +363,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     float xr[SPT], xi[SPT];
     float s_ph = 0.0f, s_aph = 0.0f, s_p2 = 0.0f, s_t2 = 0.0f;   // s_aph = sum t, t = |phi| - pi/2
     float s_f = 0.0f, s_f2 = 0.0f, s_f3 = 0.0f, s_f4 = 0.0f;
-    float tie_min = 1.0f;                                      // min | |dd| - pi | over this thread's steps
+    float tie_max = 0.0f;                                      // max |wrapped step| over this thread's steps
     const float last_keep = (t == GROUP - 1) ? 0.0f : 1.0f;   // sample N-1 has no successor
     float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -391,10 +390,8 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
         if ((j & 3) == 0) e4 = reinterpret_cast<const float4*>(edge_s)[j >> 2];   // uniform address: broadcast
         const float ej = (j & 3) == 0 ? e4.x : ((j & 3) == 1 ? e4.y : ((j & 3) == 2 ? e4.z : e4.w));
         if (lane == 31) nb = ej;
-        float dd = nb - ph;
-        const float over = fabsf(dd) - kPiF;
-        tie_min = fminf(tie_min, fabsf(over));
-        if (over > 0.0f) dd -= copysignf(kTwoPiF, dd);
+        float dd = wrap_step_f32(nb - ph);
+        tie_max = fmaxf(tie_max, fabsf(dd));
         if (j == SPT - 1) dd *= last_keep;
         s_ph += ph;
         const float tt = fabsf(ph) - kPiO2F;
@@ -409,7 +406,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
       }
     }
     if constexpr (DO_PHASE) {
-      if (tie_min < kTieEps) {   // rare (about once per 10^5 samples on noisy data)
+      if (tie_max > kPiF - kTieEps) {   // rare (about once per 10^5 samples on noisy data)
         float corr[4];
         tie_corrections16<N, CT>(xs, t, corr);
         s_f += corr[0];

@@ -118,16 +118,14 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
 #pragma unroll
       for (int j = 0; j < SPT; ++j) fq[j] = 0.0f;
     } else {
-    float tie_min = 1.0f;                                     // min | |dd| - pi | over this lane's steps
+    float tie_max = 0.0f;                                     // max |wrapped step| over this lane's steps
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
       // successor of (lane, j) is (lane+1, j); for lane 31 it is (0, j+1): lane 0 offers its next sample
       const float offer = (lane == 0) ? ph[(j + 1) % SPT] : ph[j];
       const float nb = __shfl_sync(FULL, offer, (lane + 1) & 31);
-      float dd = nb - ph[j];
-      const float over = fabsf(dd) - kPiF;
-      tie_min = fminf(tie_min, fabsf(over));
-      if (over > 0.0f) dd -= copysignf(kTwoPiF, dd);
+      float dd = wrap_step_f32(nb - ph[j]);
+      tie_max = fmaxf(tie_max, fabsf(dd));
       if (j == SPT - 1) dd *= last_keep;
       fq[j] = dd;
       s_ph += ph[j];
@@ -136,7 +134,7 @@ fusedw_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fram
       s_p2 = fmaf(ph[j], ph[j], s_p2);
       s_t2 = fmaf(tt, tt, s_t2);
     }
-    if (tie_min < kTieEps) {   // rare (about once per 10^5 samples on noisy data): FP64 re-decision, see amc_fused16.cuh
+    if (tie_max > kPiF - kTieEps) {   // rare (about once per 10^5 samples on noisy data): FP64 re-decision, see amc_fused16.cuh
       unsigned tie_mask = 0u;
 #pragma unroll
       for (int j = 0; j < SPT; ++j)

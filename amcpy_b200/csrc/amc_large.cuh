@@ -207,15 +207,9 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     float s_f2 = 0.0f, s_f3 = 0.0f, s_f4 = 0.0f;            // one-pass frequency statistics (cycles per sample)
 #pragma unroll 4
     for (int i = tid; i < N - 1; i += THREADS) {
-      float dd = phi[i + 1] - phi[i];
-      const float over = fabsf(dd) - kPiF;
-      float fj;
-      if (fabsf(over) < kTieEps) {
-        fj = exact_freq_step<CT>(x, i);
-      } else {
-        if (over > 0.0f) dd -= copysignf(kTwoPiF, dd);
-        fj = dd * kInvTwoPiF;
-      }
+      const float dd = wrap_step_f32(phi[i + 1] - phi[i]);
+      float fj = dd * kInvTwoPiF;
+      if (fabsf(dd) > kPiF - kTieEps) fj = exact_freq_step<CT>(x, i);   // rare: re-decided in float64
       s_f += fj;
       const float f2 = fj * fj;
       s_f2 += f2;
