@@ -70,17 +70,39 @@ __device__ __forceinline__ void dft4(float2& v0, float2& v1, float2& v2, float2&
   bfly2(v2, v3);
   // X0=v0 X2=v1 X1=v2 X3=v3
 }
-__device__ __forceinline__ void dft8(float2 (&v)[8]) {
+// dft4 of (a0, W8^1 a1, W8^2 a2, W8^3 a3): the 1/sqrt(2) of the two odd twiddles is not applied to them but rides on the
+// last two butterflies as fused multiply-adds (20 instructions; multiplying first takes 24).  Same output order as dft4.
+__device__ __forceinline__ void dft4_w8(float2& a0, float2& a1, float2& a2, float2& a3) {
   constexpr float h = 0.70710678118654752440f;
+  const float px = a1.x + a1.y, py = a1.y - a1.x;              // W8^1 a1 = h (px, py)
+  const float s3 = a3.x + a3.y, d3 = a3.y - a3.x;              // W8^3 a3 = h (d3, -s3)
+  const float Px = px + d3, Py = py - s3;                      // (W8^1 a1 + W8^3 a3) / h
+  const float Qx = px - d3, Qy = py + s3;                      // (W8^1 a1 - W8^3 a3) / h
+  const float2 b0 = make_float2(a0.x + a2.y, a0.y - a2.x);     // a0 + (-j) a2
+  const float2 b2 = make_float2(a0.x - a2.y, a0.y + a2.x);
+  a0 = make_float2(fmaf(h, Px, b0.x), fmaf(h, Py, b0.y));
+  a1 = make_float2(fmaf(-h, Px, b0.x), fmaf(-h, Py, b0.y));
+  a2 = make_float2(fmaf(h, Qy, b2.x), fmaf(-h, Qx, b2.y));     // b2 + (-j) h Q
+  a3 = make_float2(fmaf(-h, Qy, b2.x), fmaf(h, Qx, b2.y));
+}
+// dft4 of (a0, a1, h (ux, uy), a3); a2 is output only
+__device__ __forceinline__ void dft4_hu(float2& a0, float2& a1, float2& a2, float2& a3, float ux, float uy) {
+  constexpr float h = 0.70710678118654752440f;
+  const float2 t = a0;
+  a0 = make_float2(fmaf(h, ux, t.x), fmaf(h, uy, t.y));
+  a2 = make_float2(fmaf(-h, ux, t.x), fmaf(-h, uy, t.y));
+  bfly2(a1, a3);
+  a3 = c_mul_mj(a3);
+  bfly2(a0, a1);
+  bfly2(a2, a3);
+}
+__device__ __forceinline__ void dft8(float2 (&v)[8]) {
   bfly2(v[0], v[4]);
   bfly2(v[1], v[5]);
   bfly2(v[2], v[6]);
   bfly2(v[3], v[7]);
-  v[5] = make_float2((v[5].x + v[5].y) * h, (v[5].y - v[5].x) * h);    // * W8^1
-  v[6] = c_mul_mj(v[6]);                                               // * W8^2
-  v[7] = make_float2((v[7].y - v[7].x) * h, -(v[7].x + v[7].y) * h);   // * W8^3
   dft4(v[0], v[1], v[2], v[3]);
-  dft4(v[4], v[5], v[6], v[7]);
+  dft4_w8(v[4], v[5], v[6], v[7]);
   // X0=v0 X4=v1 X2=v2 X6=v3 X1=v4 X5=v5 X3=v6 X7=v7
 }
 // register index that holds output X_r after dft8 / dft4 / dft2

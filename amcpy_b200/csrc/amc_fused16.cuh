@@ -36,25 +36,21 @@ __device__ __forceinline__ constexpr int bitrev4(int r) {
 }
 
 // 16-point forward DFT in registers (4 x 4 Cooley-Tukey); X_r is left in v[bitrev4(r)].
+// The 1/sqrt(2) of the W16^2 / W16^6 twiddles is not applied to the values but rides on the butterflies that consume
+// them as fused multiply-adds (dft4_hu / dft4_w8, amc_fused.cuh).
 __device__ __forceinline__ void dft16(float2 (&v)[16]) {
-  constexpr float h = 0.70710678118654752440f;
   constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
 #pragma unroll
   for (int n2 = 0; n2 < 4; ++n2) dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
   // now Y[k1][n2]: k1=0 -> v[n2], k1=2 -> v[4+n2], k1=1 -> v[8+n2], k1=3 -> v[12+n2]; twiddle W16^(n2*k1)
-  v[9] = c_mul(v[9], make_float2(c1, -s1));                                  // W16^1
-  v[10] = make_float2((v[10].x + v[10].y) * h, (v[10].y - v[10].x) * h);     // W16^2
-  v[11] = c_mul(v[11], make_float2(s1, -c1));                                // W16^3
-  v[5] = make_float2((v[5].x + v[5].y) * h, (v[5].y - v[5].x) * h);          // W16^2
-  v[6] = c_mul_mj(v[6]);                                                     // W16^4
-  v[7] = make_float2((v[7].y - v[7].x) * h, -(v[7].x + v[7].y) * h);         // W16^6
-  v[13] = c_mul(v[13], make_float2(s1, -c1));                                // W16^3
-  v[14] = make_float2((v[14].y - v[14].x) * h, -(v[14].x + v[14].y) * h);    // W16^6
-  v[15] = c_mul(v[15], make_float2(-c1, s1));                                // W16^9
+  v[9] = c_mul(v[9], make_float2(c1, -s1));                                        // W16^1
+  v[11] = c_mul(v[11], make_float2(s1, -c1));                                      // W16^3
+  v[13] = c_mul(v[13], make_float2(s1, -c1));                                      // W16^3
+  v[15] = c_mul(v[15], make_float2(-c1, s1));                                      // W16^9
   dft4(v[0], v[1], v[2], v[3]);
-  dft4(v[8], v[9], v[10], v[11]);
-  dft4(v[4], v[5], v[6], v[7]);
-  dft4(v[12], v[13], v[14], v[15]);
+  dft4_hu(v[8], v[9], v[10], v[11], v[10].x + v[10].y, v[10].y - v[10].x);         // W16^2 v10 = h (x + y, y - x)
+  dft4_w8(v[4], v[5], v[6], v[7]);                                                 // W16^2, W16^4, W16^6
+  dft4_hu(v[12], v[13], v[14], v[15], v[14].y - v[14].x, -(v[14].x + v[14].y));    // W16^6 v14 = h (y - x, -(x + y))
 }
 
 // Twiddle tables of the in-place 16 x 16 x 16 Stockham stages (now used by the long-frame kernel,
@@ -161,8 +157,8 @@ struct Fused16Cfg {
   static constexpr int SLOT_BYTES = N * static_cast<int>(sizeof(CT));   // one x slot (TMA target)
   static constexpr int FFT_BYTES = N * 8;                               // stage-A output, block-wide exchange
   static constexpr int T_BYTES = W * 32 * kTRow * 8;                    // warp-private stage-B -> C exchange
-  // per (parity, warp): the 25 frame totals as doubles (index = FrameSums order, see park_and_finalize)
-  // + the three pass-1 float sums every thread needs right after the barrier (phi, |phi|, f) + pad
+  // per (parity, warp): the frame totals as doubles (index = FrameSums order, see park_and_finalize; slot 24 unused)
+  // + float slot 0: the warp's max |X_k|^2 (three more floats of padding)
   static constexpr int PART_D = kPartD16, PART_F = 4;
   static constexpr int PART_BYTES = PART_D * 8 + PART_F * 4;            // 216 per (parity, warp)
   static constexpr int EDGE_BYTES = W * 16 * 4;
@@ -278,16 +274,15 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
   auto park_and_finalize = [&](int k) {
     const int par = k & 1, bi = k % Cfg::BATCH;
     double* pe = pend + bi * kPend16Stride;
+    // spectral max: float partials (uniform addresses), selected into lane 24 without a divergent FP64 max
+    float smax = part_f(par, 0)[0];
+#pragma unroll
+    for (int w = 1; w < W; ++w) smax = fmaxf(smax, part_f(par, w)[0]);
     if (lane < kPartD16) {
       double s = part_d(par, 0)[lane];
-      if (lane == 24) {
 #pragma unroll
-        for (int w = 1; w < W; ++w) s = fmax(s, part_d(par, w)[lane]);
-      } else {
-#pragma unroll
-        for (int w = 1; w < W; ++w) s += part_d(par, w)[lane];
-      }
-      pe[lane] = s;
+      for (int w = 1; w < W; ++w) s += part_d(par, w)[lane];
+      pe[lane] = (lane == 24) ? static_cast<double>(smax) : s;
     }
     if (bi == Cfg::BATCH - 1 || k == my_frames - 1) {
       __syncwarp();
@@ -574,7 +569,7 @@ fused16_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fra
     }
     vmax = warp_max(vmax);
     }   // DO_FFT
-    if (lane == 0) part_d(par, wg)[24] = static_cast<double>(vmax);
+    if (lane == 0) part_f(par, wg)[0] = vmax;
     // no barrier here: buf_a and the partial arrays are protected by rbar (waited on in the next frame's
     // pass 1); the warp-private buffer is only touched by this warp
   }
