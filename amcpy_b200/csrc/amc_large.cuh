@@ -10,7 +10,8 @@
 // Phase / frequency statistics are ONE-PASS (round 2: raw float32 sums centred in float64 at finalisation; a frame whose
 // cancellation factor exceeds 4, or whose frequency mean exceeds 0.4 sigma, goes to the careful path) - the two-pass
 // form cost a second trip through the phase buffer and a second evaluation of every wrapped difference:
-// N = 8192 / 16384: 27.8 / 26.6 % -> 29.1 / 28.5 % of the measured HBM peak; with the |x| stash see profiles/r2_experiments.txt.
+// N = 8192 / 16384: 27.8 / 26.6 % -> 29.1 / 28.5 % of the measured HBM peak; with the |x| stash, its early read-back, the L2
+// prefetch of the next frame and the deeper unroll of the last FFT stage: 33.7 / 31.5 % (profiles/r2_experiments.txt).
 // Same tolerance classes as the fused kernels.
 #pragma once
 #include "amc_fused16.cuh"
@@ -201,6 +202,15 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
         pass1_group(gb, i0 + STEP);
       }
     }
+    // the NEXT frame of this CTA starts its trip from HBM to L2 now: pass 1b, pass 2 and the FFT (half of the frame time)
+    // leave the memory system idle, and pass 1 of the next frame then waits for L2 instead of HBM latency
+    if (f + gridDim.x < n_frames) {
+      const char* nx = reinterpret_cast<const char*>(iq + (f + gridDim.x) * frame_stride);
+      constexpr int kBytes = N * static_cast<int>(sizeof(CT));
+#pragma unroll
+      for (int o = 128 * tid; o < kBytes + 128; o += 128 * THREADS)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + min(o, kBytes - 1)));
+    }
     __syncthreads();
     // ---------------------------------------------------------------- pass 1b: sum of wrapped differences
     float s_f = 0.0f;
@@ -215,6 +225,15 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
       s_f2 += f2;
       s_f3 = fmaf(f2, fj, s_f3);
       s_f4 = fmaf(f2, f2, s_f4);
+    }
+    // pass 2 reads back what THIS thread stashed (same index set): the first half of the loads is issued here, before the
+    // reductions and the barrier, the second half when the first is consumed - one exposed L2 latency per frame, not four
+    constexpr int RPT = N / THREADS;                          // |x| values per thread: 32
+    [[maybe_unused]] double rv0[RPT / 2];
+    if constexpr (STASH) {
+      const double* r_mine = r_ws + static_cast<size_t>(blockIdx.x) * N + tid;
+#pragma unroll
+      for (int u = 0; u < RPT / 2; ++u) rv0[u] = r_mine[THREADS * u];
     }
     {
       double acc[16];
@@ -236,22 +255,17 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     // ---------------------------------------------------------------- pass 2: centred sums
     double c2acc[4] = {0.0, 0.0, 0.0, 0.0};
     if constexpr (STASH) {                                     // |x| comes back from the L2-resident scratch
-      const double* r_mine = r_ws + static_cast<size_t>(blockIdx.x) * N;
-      constexpr int U2 = 8;
-      static_assert(N % (THREADS * U2) == 0, "stash read loop");
-#pragma unroll 1
-      for (int i0 = tid; i0 < N; i0 += THREADS * U2) {
-        double rv[U2];
+      const double* r_mine = r_ws + static_cast<size_t>(blockIdx.x) * N + tid;
+      double rv1[RPT / 2];
 #pragma unroll
-        for (int u = 0; u < U2; ++u) rv[u] = r_mine[i0 + THREADS * u];
+      for (int u = 0; u < RPT / 2; ++u) rv1[u] = r_mine[THREADS * (RPT / 2 + u)];
 #pragma unroll
-        for (int u = 0; u < U2; ++u) {
-          const double d = rv[u] - mu_r;
-          const double d2 = d * d;
-          c2acc[0] += fabs(d);
-          c2acc[1] += d2;
-          c2acc[2] = fma(d2, d2, c2acc[2]);
-        }
+      for (int u = 0; u < RPT; ++u) {
+        const double d = (u < RPT / 2 ? rv0[u % (RPT / 2)] : rv1[u % (RPT / 2)]) - mu_r;
+        const double d2 = d * d;
+        c2acc[0] += fabs(d);
+        c2acc[1] += d2;
+        c2acc[2] = fma(d2, d2, c2acc[2]);
       }
     } else {                                                   // no scratch: re-read x (L2-resident), same software pipeline
       auto load_group = [&](CT (&g)[kLargeU], int i0) {
@@ -291,7 +305,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     float vmax = 0.0f;
     {
       constexpr int R4 = Cfg::R4;                                        // last stage: N/R4 = 4096 butterflies
-#pragma unroll 2
+#pragma unroll 4   // (the twiddles come from L2 - the table does not fit beside 212 KB of shared memory; 2 -> 4: +1.9 % at N = 8192)
       for (int bb = 0; bb < 4096 / THREADS; ++bb) {
         const int j = tid + THREADS * bb;
         float2 u[R4];
