@@ -11,7 +11,7 @@
 // cancellation factor exceeds 4, or whose frequency mean exceeds 0.4 sigma, goes to the careful path) - the two-pass
 // form cost a second trip through the phase buffer and a second evaluation of every wrapped difference:
 // N = 8192 / 16384: 27.8 / 26.6 % -> 29.1 / 28.5 % of the measured HBM peak; with the |x| stash, its early read-back, the L2
-// prefetch of the next frame and the deeper unroll of the last FFT stage: 33.7 / 31.5 % (profiles/r2_experiments.txt).
+// prefetch of the next frame, cache hints and the deeper unroll of the last FFT stage: 34.2 / 31.8 % (profiles/r2_experiments.txt).
 // Same tolerance classes as the fused kernels.
 #pragma once
 #include "amc_fused16.cuh"
@@ -62,6 +62,11 @@ __device__ __forceinline__ void split_sample(float2 v, double& a, double& b, flo
   a = static_cast<double>(af);
   b = static_cast<double>(bf);
 }
+// x is read once (streaming loads, evict-first) and the |x| stash lives in L2 (.cg): neither may push the FFT twiddle
+// tables out of the little L1 that is left beside the shared memory (+1 % at both sizes)
+#define AMC_LG_LDX(p) __ldcs(p)
+#define AMC_LG_STR(p, v) __stcg(p, v)
+#define AMC_LG_LDR(p) __ldcg(p)
 constexpr int kLargeU = 4;   // samples per thread per software-pipelined group (loads of group g+1 fly during group g)
 
 // one in-place radix-16 Stockham stage over the whole frame (BPT butterflies per thread).
@@ -164,7 +169,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     {
       auto load_group = [&](CT (&g)[kLargeU], int i0) {
 #pragma unroll
-        for (int u = 0; u < kLargeU; ++u) g[u] = x[i0 + THREADS * u];
+        for (int u = 0; u < kLargeU; ++u) g[u] = AMC_LG_LDX(x + i0 + THREADS * u);
       };
       float2* buf_t = buf + (tid ^ ((tid >> 4) & 15));      // swizzled position of sample tid (+ multiples of THREADS)
       [[maybe_unused]] double* r_mine = STASH ? r_ws + static_cast<size_t>(blockIdx.x) * N : nullptr;
@@ -178,7 +183,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
           const double s = mono.add(a, b);
           const double rr = sqrt_nr(s);
           sum_r += rr;
-          if constexpr (STASH) r_mine[i] = rr;
+          if constexpr (STASH) AMC_LG_STR(r_mine + i, rr);
           const float p = atan2_fast(bf, af);
           buf_t[i - tid] = make_float2(af, bf);           // = buf[swz16(i)]: (i >> 4) & 15 == (tid >> 4) & 15
           phi[i] = p;
@@ -233,7 +238,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     if constexpr (STASH) {
       const double* r_mine = r_ws + static_cast<size_t>(blockIdx.x) * N + tid;
 #pragma unroll
-      for (int u = 0; u < RPT / 2; ++u) rv0[u] = r_mine[THREADS * u];
+      for (int u = 0; u < RPT / 2; ++u) rv0[u] = AMC_LG_LDR(r_mine + THREADS * u);
     }
     {
       double acc[16];
@@ -258,7 +263,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
       const double* r_mine = r_ws + static_cast<size_t>(blockIdx.x) * N + tid;
       double rv1[RPT / 2];
 #pragma unroll
-      for (int u = 0; u < RPT / 2; ++u) rv1[u] = r_mine[THREADS * (RPT / 2 + u)];
+      for (int u = 0; u < RPT / 2; ++u) rv1[u] = AMC_LG_LDR(r_mine + THREADS * (RPT / 2 + u));
 #pragma unroll
       for (int u = 0; u < RPT; ++u) {
         const double d = (u < RPT / 2 ? rv0[u % (RPT / 2)] : rv1[u % (RPT / 2)]) - mu_r;
@@ -270,7 +275,7 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     } else {                                                   // no scratch: re-read x (L2-resident), same software pipeline
       auto load_group = [&](CT (&g)[kLargeU], int i0) {
 #pragma unroll
-        for (int u = 0; u < kLargeU; ++u) g[u] = x[i0 + THREADS * u];
+        for (int u = 0; u < kLargeU; ++u) g[u] = AMC_LG_LDX(x + i0 + THREADS * u);
       };
       auto pass2_group = [&](const CT (&g)[kLargeU]) {
 #pragma unroll
@@ -305,7 +310,8 @@ large_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t frame
     float vmax = 0.0f;
     {
       constexpr int R4 = Cfg::R4;                                        // last stage: N/R4 = 4096 butterflies
-#pragma unroll 4   // (the twiddles come from L2 - the table does not fit beside 212 KB of shared memory; 2 -> 4: +1.9 % at N = 8192)
+#pragma unroll (Cfg::R4 == 2 ? 8 : 4)
+      // (the twiddles come from L2 - the table does not fit beside 212 KB of shared memory; 2 -> 4: +1.9 % at N = 8192)
       for (int bb = 0; bb < 4096 / THREADS; ++bb) {
         const int j = tid + THREADS * bb;
         float2 u[R4];
