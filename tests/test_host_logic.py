@@ -229,3 +229,61 @@ def test_matio_planar_reader_matches_scipy_and_knows_its_limits(tmp_path):
     assert len(matio.read_planar(tmp_path / "bad.mat")) < 3
     (tmp_path / "junk.mat").write_bytes(b"not a mat file")
     assert matio.read_planar(tmp_path / "junk.mat") is None
+
+
+def test_magic_number_unwrap_step_is_the_numpy_step_away_from_ties():
+    """The float32 step the fused kernels use for np.unwrap (amc_device.cuh: wrap_step_f32 = dd - 2 pi rint(dd / 2 pi), the
+    rounding done with the 1.5 * 2^23 trick) restated in numpy: outside the tie band the kernels re-decide in float64
+    (|wrapped| within kTieEps = 4e-6 of pi) it must BE the conditional form of the reference's unwrap
+    (features.py:28 -> np.unwrap: |dd| > pi -> dd -+ 2 pi), bit for bit."""
+    rng = np.random.default_rng(5)
+    two_pi, pi, inv = np.float32(6.28318530717958647692), np.float32(3.14159265358979323846), np.float32(0.15915494309189533577)
+    magic = np.float64(12582912.0)
+    dd = np.concatenate([rng.uniform(-2 * np.pi, 2 * np.pi, 400000),
+                         np.pi + rng.uniform(-1e-4, 1e-4, 50000), -np.pi + rng.uniform(-1e-4, 1e-4, 50000),
+                         [0.0, -0.0, 6.2831, -6.2831, 3.0, -3.0]]).astype(np.float32)
+    # fmaf(dd, inv, magic): the product of two float32 is exact in float64; one rounding to float32 after the add
+    k = (dd.astype(np.float64) * np.float64(inv) + magic).astype(np.float32) - np.float32(magic)
+    assert set(np.unique(k)) <= {-1.0, 0.0, 1.0}
+    wrapped = (dd.astype(np.float64) - k.astype(np.float64) * np.float64(two_pi)).astype(np.float32)   # fmaf(k, -2 pi, dd)
+    conditional = np.where(np.abs(dd) > pi, dd - np.copysign(two_pi, dd), dd).astype(np.float32)
+    away = np.abs(pi - np.abs(wrapped)) >= np.float32(4.0e-6)
+    assert away.sum() > 400000
+    assert np.array_equal(wrapped[away].view(np.uint32), conditional[away].view(np.uint32))
+    # and inside the band both forms end within the band: the kernels' tie detection on the wrapped value sees them
+    assert np.all(np.abs(pi - np.abs(conditional[~away])) < np.float32(8.0e-6))
+
+
+def test_atan2_fast_restated_in_numpy_stays_in_the_1e6_class():
+    """amc_device.cuh: atan2_fast (degree-7 minimax in q^2 on [0, 1] + the five-instruction octant / quadrant fix-up
+    copysign(pi/2 - copysign(|r0 - [|y| <= |x|] pi/2|, x), y)) restated in float32 numpy against np.arctan2 in float64:
+    absolute error below 5e-7 over the plane, exact quadrant behaviour for signed zeros (np.angle, features.py:19)."""
+    f32 = np.float32
+    coef = [0.0026222064831683623, -0.015132382451695708, 0.0411216062546977, -0.07366684174003307,
+            0.10573921500635099, -0.14185972498001842, 0.19990396259243107, -0.33332987041851964]
+
+    def atan2_fast(y, x):
+        ax, ay = np.abs(x), np.abs(y)
+        mx = np.maximum(np.maximum(ax, ay), f32(1.0e-37))
+        q = (np.minimum(ax, ay) * (f32(1.0) / mx)).astype(f32)
+        s = (q * q).astype(f32)
+        p = np.full_like(q, f32(coef[0]))
+        for c in coef[1:]:
+            p = (p * s + f32(c)).astype(f32)
+        r0 = ((q * s).astype(f32) * p + q).astype(f32)
+        keep = np.where(ay > ax, f32(0.0), f32(1.0))
+        u = (keep * f32(-np.pi / 2) + r0).astype(f32)
+        v = np.copysign(np.abs(u), x).astype(f32)
+        r = (f32(np.pi / 2) - v).astype(f32)
+        return np.copysign(r, y).astype(f32)
+
+    rng = np.random.default_rng(9)
+    x = np.concatenate([rng.standard_normal(300000), [0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 1.0, -1.0, 0.0, 0.0, 3.0, -3.0]]).astype(f32)
+    y = np.concatenate([rng.standard_normal(300000), [0.0, 0.0, -0.0, -0.0, 1.0, 1.0, -1.0, -1.0, 2.0, -2.0, 0.0, 0.0]]).astype(f32)
+    got = atan2_fast(y, x)
+    want = np.arctan2(y.astype(np.float64), x.astype(np.float64))
+    assert np.max(np.abs(got.astype(np.float64) - want)) < 5e-7
+    # signed zeros: atan2(+0, +0) = +0, (+0, -0) = pi, (-0, +0) = -0, (-0, -0) = -pi
+    z = atan2_fast(np.array([0.0, 0.0, -0.0, -0.0], f32), np.array([0.0, -0.0, 0.0, -0.0], f32))
+    assert z[0] == 0 and not np.signbit(z[0]) and z[2] == 0 and np.signbit(z[2])
+    assert abs(z[1] - np.pi) < 1e-6 and abs(z[3] + np.pi) < 1e-6
