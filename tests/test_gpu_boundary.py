@@ -510,3 +510,47 @@ def test_concurrent_streams_with_careful_path_frames(torch_cuda):
         for o, w in zip(outs, want):
             assert torch_cuda.equal(o, w)
             assert not (o[:, 0].view(torch_cuda.int64) == 0x7ff8b200a3c10001).any()   # no tag left behind
+
+
+def test_integration_md_reference_side_binding_runs_as_printed(torch_cuda, tmp_path):
+    """INTEGRATION.md section 2 prints the ctypes stub a maintainer of the reference would paste into
+    feature_extraction.py (`_modulation_process`, :42-82) and features.py (`calculate_features`, :214-232).  The test
+    takes those two code blocks from the document as they stand, points the CDLL at the built library, runs them on a
+    small all_modulations.mat and compares with the reference's own files (golden) - the document cannot rot."""
+    import ctypes
+    import re
+    from pathlib import Path
+
+    import scipy.io
+
+    from amcpy_b200 import _native, synth
+    from amcpy_b200.config import Config, Paths, SignalConfig
+
+    text = (Path(__file__).resolve().parent.parent / "INTEGRATION.md").read_text()
+    sec = text[text.index("## 2. Patch the reference's stage"):text.index("## 3. Device-resident use")]
+    blocks = re.findall(r"```python\n(.*?)```", sec, flags=re.S)
+    assert len(blocks) == 2 and "_modulation_process" in blocks[0] and "calculate_features" in blocks[1]
+    lib_path = str(_native.build())
+    ns = {"scipy": scipy, "ctypes": ctypes, "np": np}
+    exec(blocks[0].replace('ctypes.CDLL("libamcpy_b200.so")', f"ctypes.CDLL({lib_path!r})"), ns)   # noqa: S102
+    ns["_FEATURE_FUNCTIONS"] = {i: None for i in range(1, 19)}
+    exec(blocks[1], ns)                                                                              # noqa: S102
+
+    g = load_golden("stage_16x2x2048.npz")
+    cfg = Config(paths=Paths(root=tmp_path), signals=SignalConfig(num_frames=2))
+    cfg.paths.ensure_dirs()
+    data = synth.dataset(SNRS, 2, 2048 + 8, int(g["seed"]))
+    synth.write_all_modulations_mat(cfg.paths.mat_data / cfg.paths.mat_filename, data, cfg.signals.mat_info)
+    for mod in cfg.signals.modulations_with_noise:
+        ns["_modulation_process"](mod, cfg)
+        m = scipy.io.loadmat(str(cfg.paths.calculated_features / f"{mod}_features.mat"))
+        key = cfg.signals.mat_info[mod]
+        assert m[key].dtype == np.float32 and m[key].shape == (16, 2, 18)
+        assert np.allclose(m[key].astype(np.float64), g[f"{mod}_matrix"].astype(np.float64), rtol=1.3e-6, atol=0), mod
+    # the per-frame operator of the same section: values in the order of feature_ids, KeyError on an unknown id
+    x = data[1][3, 0, :2048]
+    vals = ns["calculate_features"]([18, 1, 7], x)
+    want = g["QPSK_matrix"][3, 0].astype(np.float64)
+    assert np.allclose(vals, [want[17], want[0], want[6]], rtol=1.3e-6)
+    with pytest.raises(KeyError):
+        ns["calculate_features"]([19], x)
