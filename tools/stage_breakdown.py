@@ -1,6 +1,7 @@
 import sys, time, tempfile
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import scipy.io, torch
 from amcpy_b200 import synth, ops, matio
 from amcpy_b200 import feature_extraction as fe
 from amcpy_b200.config import Config, Paths, SignalConfig
