@@ -287,3 +287,16 @@ def test_atan2_fast_restated_in_numpy_stays_in_the_1e6_class():
     z = atan2_fast(np.array([0.0, 0.0, -0.0, -0.0], f32), np.array([0.0, -0.0, 0.0, -0.0], f32))
     assert z[0] == 0 and not np.signbit(z[0]) and z[2] == 0 and np.signbit(z[2])
     assert abs(z[1] - np.pi) < 1e-6 and abs(z[3] + np.pi) < 1e-6
+
+
+def test_integration_md_binding_blocks_are_valid_python_and_name_real_symbols(built_lib):
+    """The two code blocks of INTEGRATION.md section 2 (executed on the GPU by tests/test_gpu_boundary.py) parse, and every
+    `_lib.<symbol>` they touch is exported by the built library."""
+    text = (Path(__file__).resolve().parent.parent / "INTEGRATION.md").read_text()
+    sec = text[text.index("## 2. Patch the reference's stage"):text.index("## 3. Device-resident use")]
+    blocks = re.findall(r"```python\n(.*?)```", sec, flags=re.S)
+    assert len(blocks) == 2 and "_modulation_process" in blocks[0] and "calculate_features" in blocks[1]
+    for b in blocks:
+        ast.parse(b)
+        for sym in set(re.findall(r"_lib\.(amc_\w+)", b)):
+            assert hasattr(built_lib, sym), sym
