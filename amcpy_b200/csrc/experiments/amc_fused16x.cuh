@@ -21,6 +21,10 @@
 // phases sit in a cluster away from 0, or whose frequency has a mean above 0.4 sigma (a carrier offset of more than
 // ~0.1 cycles/sample on noisy data).  Those frames are correct, not fast.
 #pragma once
+#ifdef AMC_F16_AMP32
+// a different experiment behind the same hook of amc_api.cu: the 3-CTA kernel with float32 amplitude statistics
+#include "amc_fused16a.cuh"
+#else
 #include "../amc_fused16.cuh"
 
 namespace amc {
@@ -379,3 +383,4 @@ fused16x_features_kernel(const CT* __restrict__ iq, int64_t n_frames, int64_t fr
 }
 
 }  // namespace amc
+#endif  // AMC_F16_AMP32
